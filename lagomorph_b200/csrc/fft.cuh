@@ -1,0 +1,198 @@
+// fft.cuh -- in-shared-memory batched "column" FFTs for the FluidMetric passes.
+//
+// A tile holds L independent lines of N complex points: element (r, l) lives at
+// tile[r*rs + l*ls]. Work items are (line, sub-butterfly) pairs with the LINE
+// index fastest across lanes, so for ls == 1 every shared-memory access of a
+// warp is a run of consecutive complex words (bank-conflict free), and for the
+// transposed view (rs == 1, ls odd) the odd line pitch does the same job.
+//
+// N = r_1 * ... * r_k with radices in {2,4,8,16}; each stage is an r-point DFT
+// done entirely in registers (radix-2 DIF network, compile-time twiddles),
+// followed by the inter-stage twiddle, stored back IN PLACE. The forward
+// transform therefore leaves the spectrum in mixed-radix digit-reversed order
+// (fft_pos() gives the storage row of a frequency); the inverse consumes that
+// order and produces natural order. No reordering pass exists anywhere: the
+// Fourier multiplier looks its LUTs up in storage order.
+#pragma once
+#include "common.cuh"
+
+namespace lgm {
+
+template <typename R> struct Cx;
+template <> struct Cx<float> { using T = float2; };
+template <> struct Cx<double> { using T = double2; };
+
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+  C r;
+  r.x = a.x * b.x - a.y * b.y;
+  r.y = a.x * b.y + a.y * b.x;
+  return r;
+}
+template <typename C> __device__ __forceinline__ C cmulc(C a, C b) {  // a * conj(b)
+  C r;
+  r.x = a.x * b.x + a.y * b.y;
+  r.y = a.y * b.x - a.x * b.y;
+  return r;
+}
+
+__host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n / 2); }
+// bits of stage i when 2^b points are split into ceil(b/4) stages as evenly as possible
+__host__ __device__ constexpr int stage_bits(int b, int i) {
+  return b / ((b + 3) / 4) + (i < b % ((b + 3) / 4) ? 1 : 0);
+}
+__host__ __device__ constexpr int bitrev(int i, int bits) {
+  int r = 0;
+  for (int k = 0; k < bits; ++k) r |= ((i >> k) & 1) << (bits - 1 - k);
+  return r;
+}
+
+// storage row of frequency k after the in-place forward transform of 2^b points
+template <int N>
+__host__ __device__ __forceinline__ int fft_pos(int k) {
+  constexpr int b = ilog2(N);
+  constexpr int ns = (b + 3) / 4;
+  int pos = 0, size = N;
+#pragma unroll
+  for (int s = 0; s < ns; ++s) {
+    const int r = 1 << stage_bits(b, s);
+    size /= r;
+    pos += (k % r) * size;
+    k /= r;
+  }
+  return pos;
+}
+// runtime-N twin for the host-side LUT builder
+inline int fft_pos_rt(int N, int k) {
+  const int b = ilog2(N), ns = (b + 3) / 4;
+  int pos = 0, size = N;
+  for (int s = 0; s < ns; ++s) {
+    const int r = 1 << stage_bits(b, s);
+    size /= r;
+    pos += (k % r) * size;
+    k /= r;
+  }
+  return pos;
+}
+
+// multiply by e^{-+ 2 pi i j/16} (forward: minus), j compile-time after unrolling
+template <bool INV, typename C>
+__device__ __forceinline__ C mul_w16(C t, int j) {
+  using R = decltype(t.x);
+  const R c1 = R(0.92387953251128675613), s1 = R(0.38268343236508977173), c2 = R(0.70710678118654752440);
+  C r;
+  R wr, wi;  // w = wr - i*wi (forward), wr + i*wi (inverse)
+  switch (j) {
+    case 0: return t;
+    case 4:  // -+ i
+      if (!INV) { r.x = t.y; r.y = -t.x; } else { r.x = -t.y; r.y = t.x; }
+      return r;
+    case 2:
+      if (!INV) { r.x = c2 * (t.x + t.y); r.y = c2 * (t.y - t.x); }
+      else { r.x = c2 * (t.x - t.y); r.y = c2 * (t.y + t.x); }
+      return r;
+    case 6:
+      if (!INV) { r.x = c2 * (t.y - t.x); r.y = -c2 * (t.x + t.y); }
+      else { r.x = -c2 * (t.x + t.y); r.y = c2 * (t.x - t.y); }
+      return r;
+    case 1: wr = c1; wi = s1; break;
+    case 3: wr = s1; wi = c1; break;
+    case 5: wr = -s1; wi = c1; break;
+    default: wr = -c1; wi = s1; break;  // 7
+  }
+  if (!INV) { r.x = t.x * wr + t.y * wi; r.y = t.y * wr - t.x * wi; }
+  else { r.x = t.x * wr - t.y * wi; r.y = t.y * wr + t.x * wi; }
+  return r;
+}
+
+// RAD-point DFT in registers (radix-2 DIF). On return x[i] holds output bitrev(i).
+template <int RAD, bool INV, typename C>
+__device__ __forceinline__ void reg_fft(C (&x)[RAD]) {
+#pragma unroll
+  for (int half = RAD / 2; half >= 1; half >>= 1) {
+#pragma unroll
+    for (int base = 0; base < RAD; base += 2 * half) {
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        C a = x[base + i], b = x[base + i + half];
+        x[base + i] = cadd(a, b);
+        x[base + i + half] = mul_w16<INV>(csub(a, b), i * (8 / half));
+      }
+    }
+  }
+}
+
+// One in-place stage over blocks of BLOCK consecutive rows (BLOCK | N).
+// tw: table of N entries, tw[j] = e^{-2 pi i j / N}.
+template <typename R, int N, int BLOCK, int RAD, int L, bool INV>
+__device__ __forceinline__ void fft_stage(typename Cx<R>::T* tile, int rs, int ls,
+                                          const typename Cx<R>::T* __restrict__ tw, int tid, int nth) {
+  using C = typename Cx<R>::T;
+  constexpr int SUB = BLOCK / RAD;
+  constexpr int ITEMS = L * (N / RAD);
+  constexpr int BITS = ilog2(RAD);
+  for (int it = tid; it < ITEMS; it += nth) {
+    const int l = it % L, q = it / L;
+    const int blk = q / SUB, rest = q % SUB;
+    C* p = tile + (blk * BLOCK + rest) * rs + l * ls;
+    C x[RAD];
+    if (!INV) {
+#pragma unroll
+      for (int n = 0; n < RAD; ++n) x[n] = p[n * SUB * rs];
+      reg_fft<RAD, false>(x);
+#pragma unroll
+      for (int i = 0; i < RAD; ++i) {
+        const int k = bitrev(i, BITS);
+        C v = x[i];
+        if (SUB > 1 && k != 0) v = cmul(v, tw[rest * k * (N / BLOCK)]);
+        p[k * SUB * rs] = v;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < RAD; ++k) {
+        C v = p[k * SUB * rs];
+        if (SUB > 1 && k != 0) v = cmulc(v, tw[rest * k * (N / BLOCK)]);
+        x[k] = v;
+      }
+      reg_fft<RAD, true>(x);
+#pragma unroll
+      for (int i = 0; i < RAD; ++i) p[bitrev(i, BITS) * SUB * rs] = x[i];
+    }
+  }
+}
+
+template <typename R, int N, int BLOCK, int SI, int L>
+struct ColFFT {
+  using C = typename Cx<R>::T;
+  static constexpr int RAD = 1 << stage_bits(ilog2(N), SI);
+  static __device__ __forceinline__ void fwd(C* tile, int rs, int ls, const C* tw, int tid, int nth) {
+    fft_stage<R, N, BLOCK, RAD, L, false>(tile, rs, ls, tw, tid, nth);
+    if constexpr (BLOCK / RAD > 1) {
+      __syncthreads();
+      ColFFT<R, N, BLOCK / RAD, SI + 1, L>::fwd(tile, rs, ls, tw, tid, nth);
+    }
+  }
+  static __device__ __forceinline__ void inv(C* tile, int rs, int ls, const C* tw, int tid, int nth) {
+    if constexpr (BLOCK / RAD > 1) {
+      ColFFT<R, N, BLOCK / RAD, SI + 1, L>::inv(tile, rs, ls, tw, tid, nth);
+      __syncthreads();
+    }
+    fft_stage<R, N, BLOCK, RAD, L, true>(tile, rs, ls, tw, tid, nth);
+  }
+};
+
+// Forward / inverse (unnormalised) FFT of L lines of N points. Callers
+// __syncthreads() before (tile + tw visible) and after.
+template <typename R, int N, int L>
+__device__ __forceinline__ void col_fft_fwd(typename Cx<R>::T* tile, int rs, int ls,
+                                            const typename Cx<R>::T* tw, int tid, int nth) {
+  if constexpr (N > 1) ColFFT<R, N, N, 0, L>::fwd(tile, rs, ls, tw, tid, nth);
+}
+template <typename R, int N, int L>
+__device__ __forceinline__ void col_fft_inv(typename Cx<R>::T* tile, int rs, int ls,
+                                            const typename Cx<R>::T* tw, int tid, int nth) {
+  if constexpr (N > 1) ColFFT<R, N, N, 0, L>::inv(tile, rs, ls, tw, tid, nth);
+}
+
+}  // namespace lgm

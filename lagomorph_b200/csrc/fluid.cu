@@ -1,0 +1,867 @@
+// fluid.cu -- FluidMetric sharp/flat: batched real 2-D/3-D FFT passes with the
+// (alpha*lap + beta*grad div + gamma)^2 Fourier multiplier fused into the middle pass.
+//
+// Replaces, for the reference, torch.rfft -> lagomorph_ext.fluid_operator ->
+// torch.irfft (lagomorph/metric.py:11-19, cuda/metric.cu:162-355): no cuFFT, no
+// separate multiplier launch, no normalisation passes.
+//
+// Pass structure (3-D; 2-D drops the Y pass). Spectrum = half spectrum along the
+// last axis, Zc = Z/2+1 complex per line, kept in the digit-reversed storage
+// order the in-place FFT stages leave behind (fft.cuh):
+//   Z-fwd : real lines -> half-length complex FFT + split -> spectrum lines
+//   Y     : in-place column FFT on [Y x T] tiles (T contiguous spectrum words)
+//   X     : [X x T] tiles: forward FFT -> multiplier (all `dim` channels of one
+//           frequency together when beta != 0) -> inverse FFT, in place
+//   Y-inv, Z-inv : mirrors.
+// Sizes that are not powers of two (the reference's own tests use 3) take a
+// direct-DFT path with the same semantics (unitary scaling in the transforms,
+// multiplier on the natural-order spectrum).
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+#include "fft.cuh"
+
+namespace lgm {
+
+// ------------------------------------------------------------------------------------------
+// Fourier multiplier, arithmetic as cuda/metric.cu:162-306 (double alpha/beta/gamma, symbol
+// squared, Cholesky solve with safe_sqrt for sharp, plain multiply for flat).
+// ------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ R safe_sqrt(R x) {  // cuda/metric.cu:14-18
+  if ((double)x < 1e-8) return (R)1e-4;
+  return sqrt(x);
+}
+template <typename R>
+__device__ __forceinline__ R oo_sqrt(R x) {  // 1./safe_sqrt(x), rounded to Real
+  return (R)(1. / (double)safe_sqrt(x));
+}
+
+template <typename R, int D>
+struct Symbol {  // per-frequency operator, built once, applied to re and im parts of every sample
+  R L00, L10, L11, L20, L21, L22;
+  R ooG00, G10, ooG11, G20, G21, ooG22;
+};
+
+template <typename R, int D, bool INVERSE>
+__device__ __forceinline__ Symbol<R, D> make_symbol(const R (&w)[3], const R (&s)[3], double alpha,
+                                                    double beta, double gamma) {
+  Symbol<R, D> S;
+  if constexpr (D == 2) {
+    const R lambda = (R)(gamma + alpha * (double)(w[0] + w[1]));
+    R l00 = (R)((double)lambda - beta * (double)w[0]);
+    R l11 = (R)((double)lambda - beta * (double)w[1]);
+    R l10 = (R)(beta * (double)s[0] * (double)s[1]);
+    S.L00 = l00 * l00 + l10 * l10;
+    S.L10 = l00 * l10 + l10 * l11;
+    S.L11 = l11 * l11 + l10 * l10;
+    if (INVERSE) {
+      S.ooG00 = oo_sqrt<R>(S.L00);
+      S.G10 = S.L10 * S.ooG00;
+      S.ooG11 = oo_sqrt<R>(S.L11 - S.G10 * S.G10);
+    }
+  } else {
+    const R lambda = (R)(gamma + alpha * (double)(w[0] + w[1] + w[2]));
+    R l00 = (R)((double)lambda - beta * (double)w[0]);
+    R l11 = (R)((double)lambda - beta * (double)w[1]);
+    R l22 = (R)((double)lambda - beta * (double)w[2]);
+    R l10 = (R)(beta * (double)s[0] * (double)s[1]);
+    R l20 = (R)(beta * (double)s[0] * (double)s[2]);
+    R l21 = (R)(beta * (double)s[1] * (double)s[2]);
+    S.L00 = l00 * l00 + l10 * l10 + l20 * l20;
+    S.L10 = l00 * l10 + l10 * l11 + l20 * l21;
+    S.L11 = l10 * l10 + l11 * l11 + l21 * l21;
+    S.L20 = l00 * l20 + l10 * l21 + l20 * l22;
+    S.L21 = l10 * l20 + l11 * l21 + l21 * l22;
+    S.L22 = l20 * l20 + l21 * l21 + l22 * l22;
+    if (INVERSE) {
+      S.ooG00 = oo_sqrt<R>(S.L00);
+      S.G10 = S.L10 * S.ooG00;
+      S.G20 = S.L20 * S.ooG00;
+      S.ooG11 = oo_sqrt<R>(S.L11 - S.G10 * S.G10);
+      S.G21 = (S.L21 - S.G20 * S.G10) * S.ooG11;
+      S.ooG22 = oo_sqrt<R>(S.L22 - S.G20 * S.G20 - S.G21 * S.G21);
+    }
+  }
+  return S;
+}
+
+template <typename R, int D, bool INVERSE>
+__device__ __forceinline__ void apply_symbol(const Symbol<R, D>& S, R (&b)[D]) {
+  if constexpr (D == 2) {
+    if (INVERSE) {  // cuda/metric.cu:80-100
+      R y0 = b[0] * S.ooG00;
+      R y1 = (b[1] - S.G10 * y0) * S.ooG11;
+      b[1] = y1 * S.ooG11;
+      b[0] = (y0 - S.G10 * b[1]) * S.ooG00;
+    } else {  // :132-144
+      R x = S.L00 * b[0] + S.L10 * b[1];
+      b[1] = S.L10 * b[0] + S.L11 * b[1];
+      b[0] = x;
+    }
+  } else {
+    if (INVERSE) {  // :102-130
+      R y0 = b[0] * S.ooG00;
+      R y1 = (b[1] - S.G10 * y0) * S.ooG11;
+      R y2 = (b[2] - S.G20 * y0 - S.G21 * y1) * S.ooG22;
+      b[2] = y2 * S.ooG22;
+      b[1] = (y1 - S.G21 * b[2]) * S.ooG11;
+      b[0] = (y0 - S.G10 * b[1] - S.G20 * b[2]) * S.ooG00;
+    } else {  // :146-160
+      R x = S.L00 * b[0] + S.L10 * b[1] + S.L20 * b[2];
+      R y = S.L10 * b[0] + S.L11 * b[1] + S.L21 * b[2];
+      b[2] = S.L20 * b[0] + S.L21 * b[1] + S.L22 * b[2];
+      b[0] = x;
+      b[1] = y;
+    }
+  }
+}
+
+// beta == 0: the symbol is lambda^2 * Identity. Returns the factor pair so that
+//   sharp: v = (v*f)*f with f = 1/sqrt(lambda^2)   (what the Cholesky path reduces to)
+//   flat : v = f*v     with f = lambda^2
+template <typename R, int D, bool INVERSE>
+__device__ __forceinline__ R scalar_symbol(const R (&w)[3], double alpha, double gamma) {
+  R sw = (D == 2) ? (w[0] + w[1]) : (w[0] + w[1] + w[2]);
+  const R lambda = (R)(gamma + alpha * (double)sw);
+  const R L = lambda * lambda;
+  return INVERSE ? oo_sqrt<R>(L) : L;
+}
+
+// Standalone multiplier on a natural-order interleaved half spectrum (N, D, X, Y[, Zc], 2):
+// the reference's fluid_operator boundary, also the middle step of the direct-DFT path.
+template <typename R, int D, bool INVERSE>
+__global__ void __launch_bounds__(256)
+fluid_operator_kernel(R* __restrict__ Fm, const R* __restrict__ c0, const R* __restrict__ s0,
+                      const R* __restrict__ c1, const R* __restrict__ s1, const R* __restrict__ c2,
+                      const R* __restrict__ s2, double alpha, double beta, double gamma, int N,
+                      Geom<D> g) {
+  const long long fid = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (fid >= g.V) return;
+  int pos[D];
+  decode<D>(fid, g, pos);
+  R w[3] = {c0[pos[0]], c1[pos[1]], D == 3 ? c2[pos[D - 1]] : R(0)};
+  R s[3] = {s0[pos[0]], s1[pos[1]], D == 3 ? s2[pos[D - 1]] : R(0)};
+  Symbol<R, D> S = make_symbol<R, D, INVERSE>(w, s, alpha, beta, gamma);
+  for (int n = 0; n < N; ++n) {
+    R* base = Fm + 2 * ((long long)n * D * g.V + fid);
+    R re[D], im[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      re[c] = base[2 * c * g.V];
+      im[c] = base[2 * c * g.V + 1];
+    }
+    apply_symbol<R, D, INVERSE>(S, re);
+    apply_symbol<R, D, INVERSE>(S, im);
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      base[2 * c * g.V] = re[c];
+      base[2 * c * g.V + 1] = im[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Plan: device LUTs (storage order) and twiddle tables, cached per (device, dtype, dim, shape).
+// ------------------------------------------------------------------------------------------
+struct FluidPlan {
+  bool fast = false;
+  int dim = 0;
+  int n[3] = {1, 1, 1};
+  int rows[3] = {1, 1, 1};   // spectrum extent per axis (last axis: n/2+1)
+  void* wl[3] = {nullptr, nullptr, nullptr};  // 2(1-cos) LUT, storage order
+  void* sl[3] = {nullptr, nullptr, nullptr};  // sin LUT, storage order
+  void* tw[3] = {nullptr, nullptr, nullptr};  // e^{-2 pi i j/n}, n entries (complex)
+};
+
+static bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+
+template <typename R>
+static bool fast_ok(int dim, const int64_t* shape) {
+  const int maxn = sizeof(R) == 4 ? 512 : 256;
+  for (int a = 0; a < dim; ++a) {
+    long long n = shape[a];
+    if (!is_pow2(n)) return false;
+    if (a == dim - 1) {
+      if (n < 16 || n > 2 * maxn) return false;  // half-length complex FFT of n/2 >= 8 points
+    } else if (n < 8 || n > maxn) return false;
+  }
+  return true;
+}
+
+static std::mutex g_plan_mu;
+static std::map<std::tuple<int, int, int, long long, long long, long long>, FluidPlan> g_plans;
+
+template <typename R>
+static int get_plan(int dim, const int64_t* shape, cudaStream_t s, const FluidPlan** out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto key = std::make_tuple(dev, (int)sizeof(R), dim, (long long)shape[0], (long long)shape[1],
+                             dim == 3 ? (long long)shape[2] : 0LL);
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) {
+    *out = &it->second;
+    return LGM_OK;
+  }
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &st);
+  if (st != cudaStreamCaptureStatusNone)
+    return set_error(LGM_EUNSUP, "lgm_fluid_apply: first call for a shape builds its tables and cannot be stream-captured; call once outside capture");
+  FluidPlan p;
+  p.dim = dim;
+  p.fast = fast_ok<R>(dim, shape);
+  using C = typename Cx<R>::T;
+  for (int a = 0; a < dim; ++a) {
+    const int n = (int)shape[a];
+    const bool last = (a == dim - 1);
+    p.n[a] = n;
+    p.rows[a] = last ? n / 2 + 1 : n;
+    std::vector<R> wl(p.rows[a]), sl(p.rows[a]);
+    // frequency held by each storage row (digit-reversed on the fast path)
+    std::vector<int> freq(p.rows[a]);
+    for (int pos = 0; pos < p.rows[a]; ++pos) freq[pos] = pos;
+    if (p.fast) {
+      const int m = last ? n / 2 : n;
+      for (int k = 0; k < m; ++k) freq[fft_pos_rt(m, k)] = k;
+      if (last) freq[m] = m;
+    }
+    for (int pos = 0; pos < p.rows[a]; ++pos) {
+      // lagomorph/metric.py:65-75: float64 numpy -> torch.Tensor (float32!) -> .type(dtype)
+      const double ang = 2.0 * M_PI * (double)freq[pos] / (double)n;
+      wl[pos] = (R)(float)(2.0 * (1.0 - cos(ang)));
+      sl[pos] = (R)(float)sin(ang);
+    }
+    std::vector<C> tw(n);
+    for (int j = 0; j < n; ++j) {
+      // exact octant symmetry is not needed; cos/sin of the reduced angle in double
+      const double ang = 2.0 * M_PI * (double)j / (double)n;
+      tw[j].x = (R)cos(ang);
+      tw[j].y = (R)(-sin(ang));
+    }
+    cudaError_t e;
+    if ((e = cudaMalloc(&p.wl[a], sizeof(R) * wl.size())) != cudaSuccess ||
+        (e = cudaMalloc(&p.sl[a], sizeof(R) * sl.size())) != cudaSuccess ||
+        (e = cudaMalloc(&p.tw[a], sizeof(C) * tw.size())) != cudaSuccess)
+      return set_error((int)e, "lgm_fluid_apply: table allocation failed: %s", cudaGetErrorString(e));
+    cudaMemcpy(p.wl[a], wl.data(), sizeof(R) * wl.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.sl[a], sl.data(), sizeof(R) * sl.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.tw[a], tw.data(), sizeof(C) * tw.size(), cudaMemcpyHostToDevice);
+  }
+  auto ins = g_plans.emplace(key, p);
+  *out = &ins.first->second;
+  return LGM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast path kernels
+// ------------------------------------------------------------------------------------------
+constexpr int kFftThreads = 256;
+
+// Z forward: L real lines of Z points -> L spectrum lines of Z/2+1 words.
+template <typename R, int Z, int L>
+__global__ void __launch_bounds__(kFftThreads)
+zfwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in, long long rows_total,
+            const typename Cx<R>::T* __restrict__ tw_g) {
+  using C = typename Cx<R>::T;
+  constexpr int M = Z / 2, P = L + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* tile = reinterpret_cast<C*>(smem_raw);  // (M+1) x P
+  C* tw = tile + (M + 1) * P;                // Z entries
+  const int tid = threadIdx.x;
+  const long long row0 = (long long)blockIdx.x * L;
+  for (int j = tid; j < Z; j += kFftThreads) tw[j] = tw_g[j];
+  const C* in2 = reinterpret_cast<const C*>(in);
+  for (int idx = tid; idx < L * M; idx += kFftThreads) {
+    const int l = idx / M, j = idx % M;
+    C v;
+    v.x = v.y = R(0);
+    if (row0 + l < rows_total) v = in2[(row0 + l) * M + j];
+    tile[j * P + l] = v;
+  }
+  __syncthreads();
+  // half-length complex FFT; its twiddles W_M^j = W_Z^{2j}: pass a strided view via a table
+  // of M entries built in place over the first half would alias, so use stride-2 reads.
+  // (fft_stage indexes tw[j*(M/BLOCK)], so hand it a table compacted to M entries.)
+  C* twM = tw + Z;  // M entries, compacted
+  for (int j = tid; j < M; j += kFftThreads) twM[j] = tw[2 * j];
+  __syncthreads();
+  col_fft_fwd<R, M, L>(tile, P, 1, twM, tid, kFftThreads);
+  __syncthreads();
+  // split: X[k] = 1/2[(Zk + conj Z(M-k)) - i W_Z^k (Zk - conj Z(M-k))]
+  for (int idx = tid; idx < L * (M / 2 + 1); idx += kFftThreads) {
+    const int l = idx % L, k = idx / L;
+    if (k == 0) {
+      C a = tile[l];  // fft_pos(0) == 0
+      C x0, xm;
+      x0.x = a.x + a.y; x0.y = R(0);
+      xm.x = a.x - a.y; xm.y = R(0);
+      tile[l] = x0;
+      tile[M * P + l] = xm;
+    } else {
+      const int pa = fft_pos<M>(k), pb = fft_pos<M>(M - k);
+      C a = tile[pa * P + l], b = tile[pb * P + l], w = tw[k];
+      C s, d, t, xk, xm;
+      s.x = a.x + b.x; s.y = a.y - b.y;
+      d.x = a.x - b.x; d.y = a.y + b.y;
+      t = cmul(w, d);
+      xk.x = R(0.5) * (s.x + t.y);
+      xk.y = R(0.5) * (s.y - t.x);
+      // partner: s' = conj(s), d' = (-d.x, d.y), w' = (-w.x, w.y)
+      C w2, d2, t2;
+      w2.x = -w.x; w2.y = w.y;
+      d2.x = -d.x; d2.y = d.y;
+      t2 = cmul(w2, d2);
+      xm.x = R(0.5) * (s.x + t2.y);
+      xm.y = R(0.5) * (-s.y - t2.x);
+      tile[pa * P + l] = xk;
+      if (pb != pa) tile[pb * P + l] = xm;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < L * (M + 1); idx += kFftThreads) {
+    const int l = idx / (M + 1), p = idx % (M + 1);
+    if (row0 + l < rows_total) spec[(row0 + l) * (M + 1) + p] = tile[p * P + l];
+  }
+}
+
+// Z inverse: spectrum lines -> real lines (unnormalised; scaling lives in the multiplier).
+template <typename R, int Z, int L>
+__global__ void __launch_bounds__(kFftThreads)
+zinv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec, long long rows_total,
+            const typename Cx<R>::T* __restrict__ tw_g) {
+  using C = typename Cx<R>::T;
+  constexpr int M = Z / 2, P = L + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* tile = reinterpret_cast<C*>(smem_raw);
+  C* tw = tile + (M + 1) * P;
+  C* twM = tw + Z;
+  const int tid = threadIdx.x;
+  const long long row0 = (long long)blockIdx.x * L;
+  for (int j = tid; j < Z; j += kFftThreads) tw[j] = tw_g[j];
+  for (int j = tid; j < M; j += kFftThreads) twM[j] = tw_g[2 * j];
+  for (int idx = tid; idx < L * (M + 1); idx += kFftThreads) {
+    const int l = idx / (M + 1), p = idx % (M + 1);
+    C v;
+    v.x = v.y = R(0);
+    if (row0 + l < rows_total) v = spec[(row0 + l) * (M + 1) + p];
+    tile[p * P + l] = v;
+  }
+  __syncthreads();
+  // unsplit: Z'[k] = (Xk + conj X(M-k)) + i conj(W^k) (Xk - conj X(M-k))
+  for (int idx = tid; idx < L * (M / 2 + 1); idx += kFftThreads) {
+    const int l = idx % L, k = idx / L;
+    if (k == 0) {
+      R r0 = tile[l].x, rm = tile[M * P + l].x;  // imaginary parts of DC/Nyquist are ignored (C2R)
+      C z;
+      z.x = r0 + rm;
+      z.y = r0 - rm;
+      tile[l] = z;
+    } else {
+      const int pa = fft_pos<M>(k), pb = fft_pos<M>(M - k);
+      C a = tile[pa * P + l], b = tile[pb * P + l], w = tw[k];
+      C s, d, t, zk, zm;
+      s.x = a.x + b.x; s.y = a.y - b.y;   // Xk + conj Xm
+      d.x = a.x - b.x; d.y = a.y + b.y;   // Xk - conj Xm
+      t = cmulc(d, w);                    // conj(w) * d
+      zk.x = s.x - t.y;                   // + i*t
+      zk.y = s.y + t.x;
+      // partner: s' = conj(s), d' = (-d.x, d.y), factor i * (-w)
+      C d2, t2;
+      d2.x = -d.x; d2.y = d.y;
+      t2 = cmul(d2, w);
+      zm.x = s.x + t2.y;                  // - i*t2
+      zm.y = -s.y - t2.x;
+      tile[pa * P + l] = zk;
+      if (pb != pa) tile[pb * P + l] = zm;
+    }
+  }
+  __syncthreads();
+  col_fft_inv<R, M, L>(tile, P, 1, twM, tid, kFftThreads);
+  __syncthreads();
+  C* out2 = reinterpret_cast<C*>(out);
+  for (int idx = tid; idx < L * M; idx += kFftThreads) {
+    const int l = idx / M, j = idx % M;
+    if (row0 + l < rows_total) out2[(row0 + l) * M + j] = tile[j * P + l];
+  }
+}
+
+// Y pass (3-D only): in-place column FFT over the middle axis on [NY x T] tiles.
+// grid = (ceil(Zc/T), X, N*dim)
+template <typename R, int NY, int T, bool INV>
+__global__ void __launch_bounds__(kFftThreads)
+ypass_kernel(typename Cx<R>::T* __restrict__ spec, int X, int Zc,
+             const typename Cx<R>::T* __restrict__ tw_g) {
+  using C = typename Cx<R>::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* tile = reinterpret_cast<C*>(smem_raw);  // NY x T
+  C* tw = tile + NY * T;
+  const int tid = threadIdx.x;
+  for (int j = tid; j < NY; j += kFftThreads) tw[j] = tw_g[j];
+  const int z0 = blockIdx.x * T;
+  C* base = spec + (((long long)blockIdx.z * X + blockIdx.y) * NY) * Zc + z0;
+  for (int idx = tid; idx < NY * T; idx += kFftThreads) {
+    const int l = idx % T, r = idx / T;
+    C v;
+    v.x = v.y = R(0);
+    if (z0 + l < Zc) v = base[(long long)r * Zc + l];
+    tile[idx] = v;
+  }
+  __syncthreads();
+  if (!INV) col_fft_fwd<R, NY, T>(tile, T, 1, tw, tid, kFftThreads);
+  else col_fft_inv<R, NY, T>(tile, T, 1, tw, tid, kFftThreads);
+  __syncthreads();
+  for (int idx = tid; idx < NY * T; idx += kFftThreads) {
+    const int l = idx % T, r = idx / T;
+    if (z0 + l < Zc) base[(long long)r * Zc + l] = tile[idx];
+  }
+}
+
+// X pass with the multiplier: tiles of T consecutive words of the (Y x Zc) plane (contiguous
+// for fixed x), all NX rows. NCH = 1 (beta == 0: channels independent, grid.y = N*dim) or
+// NCH = dim (beta != 0: the dim channels of a subject together, grid.y = N).
+template <typename R, int NX, int T, int D, int NCH, bool INVERSE>
+__global__ void __launch_bounds__(kFftThreads)
+xpass_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
+             const typename Cx<R>::T* __restrict__ tw_g, const R* __restrict__ wl0,
+             const R* __restrict__ sl0, const R* __restrict__ wl1, const R* __restrict__ sl1,
+             const R* __restrict__ wl2, const R* __restrict__ sl2, double alpha, double beta,
+             double gamma, R scale) {
+  using C = typename Cx<R>::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* tile = reinterpret_cast<C*>(smem_raw);  // NCH x NX x T
+  C* tw = tile + NCH * NX * T;
+  const int tid = threadIdx.x;
+  for (int j = tid; j < NX; j += kFftThreads) tw[j] = tw_g[j];
+  const long long q0 = (long long)blockIdx.x * T;
+  C* base = spec + (long long)blockIdx.y * NCH * NX * plane + q0;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch)
+    for (int idx = tid; idx < NX * T; idx += kFftThreads) {
+      const int l = idx % T, r = idx / T;
+      C v;
+      v.x = v.y = R(0);
+      if (q0 + l < plane) v = base[((long long)ch * NX + r) * plane + l];
+      tile[ch * NX * T + idx] = v;
+    }
+  __syncthreads();
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    col_fft_fwd<R, NX, T>(tile + ch * NX * T, T, 1, tw, tid, kFftThreads);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NX * T; idx += kFftThreads) {
+    const int l = idx % T, r = idx / T;
+    const long long q = q0 + l;
+    if (q >= plane) continue;
+    R w[3], s[3];
+    w[0] = wl0[r];
+    s[0] = sl0[r];
+    if constexpr (D == 2) {
+      w[1] = wl1[q]; s[1] = sl1[q];
+      w[2] = R(0); s[2] = R(0);
+    } else {
+      const int py = (int)(q / Zc), pz = (int)(q - (long long)py * Zc);
+      w[1] = wl1[py]; s[1] = sl1[py];
+      w[2] = wl2[pz]; s[2] = sl2[pz];
+    }
+    if constexpr (NCH == 1) {
+      const R f = scalar_symbol<R, D, INVERSE>(w, alpha, gamma);
+      C v = tile[idx];
+      if (INVERSE) { v.x = ((v.x * f) * f) * scale; v.y = ((v.y * f) * f) * scale; }
+      else { v.x = (f * v.x) * scale; v.y = (f * v.y) * scale; }
+      tile[idx] = v;
+    } else {
+      Symbol<R, D> S = make_symbol<R, D, INVERSE>(w, s, alpha, beta, gamma);
+      R re[D], im[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        C v = tile[c * NX * T + idx];
+        re[c] = v.x;
+        im[c] = v.y;
+      }
+      apply_symbol<R, D, INVERSE>(S, re);
+      apply_symbol<R, D, INVERSE>(S, im);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        C v;
+        v.x = re[c] * scale;
+        v.y = im[c] * scale;
+        tile[c * NX * T + idx] = v;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    col_fft_inv<R, NX, T>(tile + ch * NX * T, T, 1, tw, tid, kFftThreads);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch)
+    for (int idx = tid; idx < NX * T; idx += kFftThreads) {
+      const int l = idx % T, r = idx / T;
+      if (q0 + l < plane) base[((long long)ch * NX + r) * plane + l] = tile[ch * NX * T + idx];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Direct-DFT path (any size): unitary transforms, out of place between two buffers.
+// ------------------------------------------------------------------------------------------
+// real lines (rows x n) -> (rows x nc) complex, scaled
+template <typename R>
+__global__ void dft_r2c_kernel(typename Cx<R>::T* __restrict__ out, const R* __restrict__ in,
+                               long long rows, int n, int nc, const typename Cx<R>::T* __restrict__ tw,
+                               R scale) {
+  using C = typename Cx<R>::T;
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= rows * nc) return;
+  const long long row = id / nc;
+  const int k = (int)(id - row * nc);
+  R ar = 0, ai = 0;
+  for (int j = 0; j < n; ++j) {
+    C w = tw[(int)(((long long)j * k) % n)];
+    R x = in[row * n + j];
+    ar += x * w.x;
+    ai += x * w.y;
+  }
+  C o;
+  o.x = ar * scale;
+  o.y = ai * scale;
+  out[id] = o;
+}
+// complex lines along an axis of length n with element stride `st` (inner count = st):
+// element index = (outer*n + j)*st + inner
+template <typename R, bool INV>
+__global__ void dft_c2c_kernel(typename Cx<R>::T* __restrict__ out,
+                               const typename Cx<R>::T* __restrict__ in, long long total, int n,
+                               long long st, const typename Cx<R>::T* __restrict__ tw, R scale) {
+  using C = typename Cx<R>::T;
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= total) return;
+  const long long inner = id % st;
+  const long long t = id / st;
+  const int k = (int)(t % n);
+  const long long outer = t / n;
+  const C* line = in + outer * n * st + inner;
+  R ar = 0, ai = 0;
+  for (int j = 0; j < n; ++j) {
+    C w = tw[(int)(((long long)j * k) % n)];
+    if (INV) w.y = -w.y;
+    C x = line[(long long)j * st];
+    ar += x.x * w.x - x.y * w.y;
+    ai += x.x * w.y + x.y * w.x;
+  }
+  C o;
+  o.x = ar * scale;
+  o.y = ai * scale;
+  out[id] = o;
+}
+// (rows x nc) half spectrum -> real lines (rows x n); imaginary parts of DC/Nyquist ignored
+template <typename R>
+__global__ void dft_c2r_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ in,
+                               long long rows, int n, int nc, const typename Cx<R>::T* __restrict__ tw,
+                               R scale) {
+  using C = typename Cx<R>::T;
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= rows * n) return;
+  const long long row = id / n;
+  const int j = (int)(id - row * n);
+  const C* line = in + row * nc;
+  R acc = line[0].x;
+  for (int k = 1; k < nc; ++k) {
+    C w = tw[(int)(((long long)j * k) % n)];  // e^{-i th}; need Re(X e^{+i th})
+    C x = line[k];
+    R term = x.x * w.x + x.y * w.y;
+    if (2 * k == n) acc += x.x * w.x;  // Nyquist: real, counted once
+    else acc += R(2) * term;
+  }
+  out[id] = acc * scale;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host drivers
+// ------------------------------------------------------------------------------------------
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+#define LGM_CUDA_TRY(expr, what)                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) return set_error((int)e__, "%s: %s", what, cudaGetErrorString(e__)); \
+  } while (0)
+
+template <typename R>
+struct FastLaunch {
+  using C = typename Cx<R>::T;
+  static constexpr int ZL = 32;                        // lines per CTA in the Z passes
+  static constexpr int T = sizeof(R) == 4 ? 16 : 8;    // tile width of the Y / X passes
+
+  template <int Z>
+  static int zfwd(C* spec, const R* in, long long rows, const C* tw, cudaStream_t s) {
+    constexpr int M = Z / 2;
+    const size_t smem = sizeof(C) * ((size_t)(M + 1) * (ZL + 1) + Z + M);
+    LGM_CUDA_TRY(set_smem(zfwd_kernel<R, Z, ZL>, smem), "zfwd smem");
+    zfwd_kernel<R, Z, ZL><<<(unsigned)cdiv(rows, ZL), kFftThreads, smem, s>>>(spec, in, rows, tw);
+    count_launch();
+    return LGM_OK;
+  }
+  template <int Z>
+  static int zinv(R* out, const C* spec, long long rows, const C* tw, cudaStream_t s) {
+    constexpr int M = Z / 2;
+    const size_t smem = sizeof(C) * ((size_t)(M + 1) * (ZL + 1) + Z + M);
+    LGM_CUDA_TRY(set_smem(zinv_kernel<R, Z, ZL>, smem), "zinv smem");
+    zinv_kernel<R, Z, ZL><<<(unsigned)cdiv(rows, ZL), kFftThreads, smem, s>>>(out, spec, rows, tw);
+    count_launch();
+    return LGM_OK;
+  }
+  template <int NY, bool INV>
+  static int ypass(C* spec, int NC, int X, int Zc, const C* tw, cudaStream_t s) {
+    const size_t smem = sizeof(C) * ((size_t)NY * T + NY);
+    LGM_CUDA_TRY(set_smem(ypass_kernel<R, NY, T, INV>, smem), "ypass smem");
+    dim3 grid((unsigned)cdiv(Zc, T), (unsigned)X, (unsigned)NC);
+    ypass_kernel<R, NY, T, INV><<<grid, kFftThreads, smem, s>>>(spec, X, Zc, tw);
+    count_launch();
+    return LGM_OK;
+  }
+  template <int NX, int D, int NCH, bool INVERSE>
+  static int xpass1(C* spec, long long N, long long plane, int Zc, const FluidPlan& p, double alpha,
+                    double beta, double gamma, R scale, cudaStream_t s) {
+    const size_t smem = sizeof(C) * ((size_t)NCH * NX * T + NX);
+    LGM_CUDA_TRY(set_smem(xpass_kernel<R, NX, T, D, NCH, INVERSE>, smem), "xpass smem");
+    dim3 grid((unsigned)cdiv(plane, T), (unsigned)(NCH == 1 ? N * D : N));
+    xpass_kernel<R, NX, T, D, NCH, INVERSE><<<grid, kFftThreads, smem, s>>>(
+        spec, plane, Zc, (const C*)p.tw[0], (const R*)p.wl[0], (const R*)p.sl[0], (const R*)p.wl[1],
+        (const R*)p.sl[1], (const R*)p.wl[2], (const R*)p.sl[2], alpha, beta, gamma, scale);
+    count_launch();
+    return LGM_OK;
+  }
+  template <int NX, int D>
+  static int xpass(C* spec, long long N, long long plane, int Zc, const FluidPlan& p, int inverse,
+                   double alpha, double beta, double gamma, R scale, cudaStream_t s) {
+    if (beta == 0.0) {
+      return inverse ? xpass1<NX, D, 1, true>(spec, N, plane, Zc, p, alpha, beta, gamma, scale, s)
+                     : xpass1<NX, D, 1, false>(spec, N, plane, Zc, p, alpha, beta, gamma, scale, s);
+    }
+    return inverse ? xpass1<NX, D, D, true>(spec, N, plane, Zc, p, alpha, beta, gamma, scale, s)
+                   : xpass1<NX, D, D, false>(spec, N, plane, Zc, p, alpha, beta, gamma, scale, s);
+  }
+};
+
+// size switches ------------------------------------------------------------------------------
+#define LGM_SWITCH_POW2(n, MAXN, CALL)                     \
+  switch (n) {                                             \
+    case 8: { constexpr int NN = 8; CALL; } break;         \
+    case 16: { constexpr int NN = 16; CALL; } break;       \
+    case 32: { constexpr int NN = 32; CALL; } break;       \
+    case 64: { constexpr int NN = 64; CALL; } break;       \
+    case 128: { constexpr int NN = 128; CALL; } break;     \
+    case 256: { constexpr int NN = 256; CALL; } break;     \
+    case 512: if constexpr (MAXN >= 512) { constexpr int NN = 512; CALL; } break; \
+    default: break;                                        \
+  }
+#define LGM_SWITCH_Z(n, MAXN, CALL)                        \
+  switch (n) {                                             \
+    case 16: { constexpr int NN = 16; CALL; } break;       \
+    case 32: { constexpr int NN = 32; CALL; } break;       \
+    case 64: { constexpr int NN = 64; CALL; } break;       \
+    case 128: { constexpr int NN = 128; CALL; } break;     \
+    case 256: { constexpr int NN = 256; CALL; } break;     \
+    case 512: { constexpr int NN = 512; CALL; } break;     \
+    case 1024: if constexpr (MAXN >= 512) { constexpr int NN = 1024; CALL; } break; \
+    default: break;                                        \
+  }
+
+template <typename R>
+static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64_t* shape,
+                      int inverse, double alpha, double beta, double gamma, void* ws,
+                      const FluidPlan& p, cudaStream_t s) {
+  using C = typename Cx<R>::T;
+  using FL = FastLaunch<R>;
+  constexpr int MAXN = sizeof(R) == 4 ? 512 : 256;
+  const int X = (int)shape[0], Y = (int)shape[1], Z = dim == 3 ? (int)shape[2] : 0;
+  const int nlast = (int)shape[dim - 1];
+  const int Zc = nlast / 2 + 1;
+  long long V = 1;
+  for (int a = 0; a < dim; ++a) V *= shape[a];
+  const long long rows = N * dim * (V / nlast);
+  C* spec = (C*)ws;
+  const R scale = (R)(1.0 / (double)V);
+  int rc = LGM_EUNSUP;
+  LGM_SWITCH_Z(nlast, MAXN, rc = FL::template zfwd<NN>(spec, (const R*)in, rows, (const C*)p.tw[dim - 1], s));
+  if (rc) return rc == LGM_EUNSUP ? set_error(rc, "lgm_fluid_apply: unsupported size") : rc;
+  if (dim == 3) {
+    rc = LGM_EUNSUP;
+    LGM_SWITCH_POW2(Y, MAXN, rc = (FL::template ypass<NN, false>(spec, (int)(N * dim), X, Zc, (const C*)p.tw[1], s)));
+    if (rc) return rc;
+    rc = LGM_EUNSUP;
+    LGM_SWITCH_POW2(X, MAXN, rc = (FL::template xpass<NN, 3>(spec, N, (long long)Y * Zc, Zc, p, inverse, alpha, beta, gamma, scale, s)));
+    if (rc) return rc;
+    rc = LGM_EUNSUP;
+    LGM_SWITCH_POW2(Y, MAXN, rc = (FL::template ypass<NN, true>(spec, (int)(N * dim), X, Zc, (const C*)p.tw[1], s)));
+    if (rc) return rc;
+  } else {
+    rc = LGM_EUNSUP;
+    LGM_SWITCH_POW2(X, MAXN, rc = (FL::template xpass<NN, 2>(spec, N, (long long)Zc, Zc, p, inverse, alpha, beta, gamma, scale, s)));
+    if (rc) return rc;
+  }
+  (void)Z;
+  rc = LGM_EUNSUP;
+  LGM_SWITCH_Z(nlast, MAXN, rc = FL::template zinv<NN>((R*)out, spec, rows, (const C*)p.tw[dim - 1], s));
+  return rc;
+}
+
+template <typename R, int D>
+static void launch_operator(R* Fm, int inverse, const FluidPlan& p, double alpha, double beta,
+                            double gamma, int N, const Geom<D>& g, cudaStream_t s) {
+  const unsigned blocks = (unsigned)cdiv(g.V, 256);
+  if (inverse)
+    fluid_operator_kernel<R, D, true><<<blocks, 256, 0, s>>>(Fm, (const R*)p.wl[0], (const R*)p.sl[0], (const R*)p.wl[1], (const R*)p.sl[1], (const R*)p.wl[2], (const R*)p.sl[2], alpha, beta, gamma, N, g);
+  else
+    fluid_operator_kernel<R, D, false><<<blocks, 256, 0, s>>>(Fm, (const R*)p.wl[0], (const R*)p.sl[0], (const R*)p.wl[1], (const R*)p.sl[1], (const R*)p.wl[2], (const R*)p.sl[2], alpha, beta, gamma, N, g);
+  count_launch();
+}
+
+template <typename R>
+static int fluid_naive(void* out, const void* in, int64_t N, int dim, const int64_t* shape,
+                       int inverse, double alpha, double beta, double gamma, void* ws,
+                       const FluidPlan& p, cudaStream_t s) {
+  using C = typename Cx<R>::T;
+  const int nlast = (int)shape[dim - 1], nc = nlast / 2 + 1;
+  long long V = 1;
+  for (int a = 0; a < dim; ++a) V *= shape[a];
+  const long long lines = N * dim * (V / nlast);   // real lines
+  const long long S = lines * nc;                  // spectrum words
+  C* A = (C*)ws;
+  C* B = A + S;
+  const R sc = (R)(1.0 / sqrt((double)V));
+  const int th = 256;
+  dft_r2c_kernel<R><<<(unsigned)cdiv(S, th), th, 0, s>>>(A, (const R*)in, lines, nlast, nc, (const C*)p.tw[dim - 1], sc);
+  count_launch();
+  C* cur = A;
+  C* oth = B;
+  // remaining axes from the second-to-last to the first
+  long long st = nc;
+  for (int a = dim - 2; a >= 0; --a) {
+    dft_c2c_kernel<R, false><<<(unsigned)cdiv(S, th), th, 0, s>>>(oth, cur, S, (int)shape[a], st, (const C*)p.tw[a], R(1));
+    count_launch();
+    C* t = cur; cur = oth; oth = t;
+    st *= shape[a];
+  }
+  int64_t sshape[3];
+  for (int a = 0; a < dim; ++a) sshape[a] = shape[a];
+  sshape[dim - 1] = nc;
+  if (dim == 2) launch_operator<R, 2>((R*)cur, inverse, p, alpha, beta, gamma, (int)N, make_geom<2>(sshape), s);
+  else launch_operator<R, 3>((R*)cur, inverse, p, alpha, beta, gamma, (int)N, make_geom<3>(sshape), s);
+  st = nc;
+  for (int a = dim - 2; a >= 0; --a) {
+    dft_c2c_kernel<R, true><<<(unsigned)cdiv(S, th), th, 0, s>>>(oth, cur, S, (int)shape[a], st, (const C*)p.tw[a], R(1));
+    count_launch();
+    C* t = cur; cur = oth; oth = t;
+    st *= shape[a];
+  }
+  dft_c2r_kernel<R><<<(unsigned)cdiv(lines * nlast, th), th, 0, s>>>((R*)out, cur, lines, nlast, nc, (const C*)p.tw[dim - 1], sc);
+  count_launch();
+  return LGM_OK;
+}
+
+template <typename R>
+static int64_t fluid_ws_bytes(int64_t N, int dim, const int64_t* shape) {
+  long long V = 1;
+  for (int a = 0; a < dim; ++a) V *= shape[a];
+  const long long nlast = shape[dim - 1];
+  if (V == 0 || N == 0) return 0;
+  const long long S = N * dim * (V / nlast) * (nlast / 2 + 1);
+  const int bufs = fast_ok<R>(dim, shape) ? 1 : 2;
+  return (int64_t)(S * 2 * sizeof(R) * bufs);
+}
+
+template <typename R>
+int fluid_apply_t(void* out, const void* in, int64_t N, int dim, const int64_t* shape, int inverse,
+                  double alpha, double beta, double gamma, void* ws, int64_t ws_bytes,
+                  cudaStream_t s) {
+  if (N == 0) return LGM_OK;
+  for (int a = 0; a < dim; ++a)
+    if (shape[a] <= 0) return LGM_OK;
+  if (ws_bytes < fluid_ws_bytes<R>(N, dim, shape))
+    return set_error(LGM_ENOSPC, "lgm_fluid_apply: workspace too small (%lld < %lld bytes)",
+                     (long long)ws_bytes, (long long)fluid_ws_bytes<R>(N, dim, shape));
+  const FluidPlan* p = nullptr;
+  int rc = get_plan<R>(dim, shape, s, &p);
+  if (rc) return rc;
+  if (p->fast) {
+    if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws) & 15)
+      return set_error(LGM_EINVAL, "lgm_fluid_apply: pointers must be 16-byte aligned");
+    rc = fluid_fast<R>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, *p, s);
+  } else {
+    rc = fluid_naive<R>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, *p, s);
+  }
+  if (rc) return rc;
+  return finish(s, "lgm_fluid_apply");
+}
+
+template int fluid_apply_t<float>(void*, const void*, int64_t, int, const int64_t*, int, double, double, double, void*, int64_t, cudaStream_t);
+template int fluid_apply_t<double>(void*, const void*, int64_t, int, const int64_t*, int, double, double, double, void*, int64_t, cudaStream_t);
+
+int64_t fluid_workspace_bytes(int dtype, int64_t N, int dim, const int64_t* shape) {
+  return dtype == LGM_F32 ? fluid_ws_bytes<float>(N, dim, shape) : fluid_ws_bytes<double>(N, dim, shape);
+}
+
+}  // namespace lgm
+
+using namespace lgm;
+
+extern "C" int64_t lgm_fluid_workspace_bytes(int dtype, int64_t N, int dim, const int64_t* shape) {
+  if ((dim != 2 && dim != 3) || (dtype != LGM_F32 && dtype != LGM_F64)) return -1;
+  return fluid_workspace_bytes(dtype, N, dim, shape);
+}
+
+extern "C" int lgm_fluid_apply(int dtype, void* out, const void* in, int64_t N, int dim,
+                               const int64_t* shape, int inverse, double alpha, double beta,
+                               double gamma, void* workspace, int64_t workspace_bytes, void* stream) {
+  LGM_REQUIRE(dim == 2 || dim == 3, "Only two- and three-dimensional fluid metric is supported");
+  LGM_REQUIRE(N >= 0 && N <= 21845, "lgm_fluid_apply: batch size out of range");
+  if (dtype == LGM_F32)
+    return fluid_apply_t<float>(out, in, N, dim, shape, inverse, alpha, beta, gamma, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (dtype == LGM_F64)
+    return fluid_apply_t<double>(out, in, N, dim, shape, inverse, alpha, beta, gamma, workspace, workspace_bytes, (cudaStream_t)stream);
+  return set_error(LGM_EINVAL, "lgm_fluid_apply: unsupported dtype %d", dtype);
+}
+
+template <typename R>
+static int fluid_operator_t(void* Fm, int inverse, const void* const* cl, const void* const* sl,
+                            double alpha, double beta, double gamma, int64_t N, int dim,
+                            const int64_t* spec_shape, cudaStream_t s) {
+  FluidPlan p;
+  for (int a = 0; a < dim; ++a) {
+    p.wl[a] = const_cast<void*>(cl[a]);
+    p.sl[a] = const_cast<void*>(sl[a]);
+  }
+  if (dim == 2) {
+    Geom<2> g = make_geom<2>(spec_shape);
+    if (g.V == 0 || N == 0) return LGM_OK;
+    launch_operator<R, 2>((R*)Fm, inverse, p, alpha, beta, gamma, (int)N, g, s);
+  } else {
+    Geom<3> g = make_geom<3>(spec_shape);
+    if (g.V == 0 || N == 0) return LGM_OK;
+    launch_operator<R, 3>((R*)Fm, inverse, p, alpha, beta, gamma, (int)N, g, s);
+  }
+  return finish(s, "lgm_fluid_operator");
+}
+
+extern "C" int lgm_fluid_operator(int dtype, void* Fm, int inverse, const void* const* cos_luts,
+                                  const void* const* sin_luts, double alpha, double beta,
+                                  double gamma, int64_t N, int dim, const int64_t* spec_shape,
+                                  void* stream) {
+  LGM_REQUIRE(dim == 2 || dim == 3, "Only two- and three-dimensional fluid metric is supported");
+  if (dtype == LGM_F32)
+    return fluid_operator_t<float>(Fm, inverse, cos_luts, sin_luts, alpha, beta, gamma, N, dim, spec_shape, (cudaStream_t)stream);
+  if (dtype == LGM_F64)
+    return fluid_operator_t<double>(Fm, inverse, cos_luts, sin_luts, alpha, beta, gamma, N, dim, spec_shape, (cudaStream_t)stream);
+  return set_error(LGM_EINVAL, "lgm_fluid_operator: unsupported dtype %d", dtype);
+}
