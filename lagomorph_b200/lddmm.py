@@ -1,0 +1,146 @@
+"""LDDMM vector-momentum geodesic shooting (mirror of lagomorph/lddmm.py:20-105)."""
+import math
+
+import torch
+
+from . import _lib as L
+from . import adjrep, deform
+from .metric import FluidMetric
+
+
+def expmap_advect(metric, m, T=1.0, num_steps=10, phiinv=None):
+    """EPDiff without the integrated form: Euler steps of d/dt m = -ad_v^* m (lddmm.py:20-36)."""
+    if phiinv is None:
+        phiinv = torch.zeros_like(m)
+    dt = T / num_steps
+    v = metric.sharp(m)
+    phiinv = deform.compose_disp_vel(phiinv, v, dt=-dt)
+    for i in range(num_steps - 1):
+        m = m - dt * adjrep.ad_star(v, m)
+        v = metric.sharp(m)
+        phiinv = deform.compose_disp_vel(phiinv, v, dt=-dt)
+    return phiinv
+
+
+def _needs_grad(*ts):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
+class _StepWorkspace:
+    """Scratch for lgm_epdiff_step_fwd, reused across the steps of one shoot."""
+
+    def __init__(self, m0):
+        self.dev = m0.device
+        self.d = L.spatial_dim(m0)
+        self.N = m0.shape[0]
+        self.sh = L.shape_arr(m0.shape[2:])
+        self.code = L.dtype_code(m0)
+        self.nbytes = int(L.lib.lgm_epdiff_scratch_bytes(self.code, self.N, self.d, self.sh))
+        if self.nbytes < 0:
+            raise RuntimeError("lgm_epdiff_scratch_bytes rejected the arguments")
+        self.buf = torch.empty(max(self.nbytes, 16), dtype=torch.uint8, device=self.dev)
+
+
+def _fused_step(metric, m0, dt, phiinv, mommask, ws, out):
+    alpha, beta, gamma = [float(p) for p in metric.params]
+    with torch.cuda.device(ws.dev):
+        L.check(L.lib.lgm_epdiff_step_fwd(ws.code, L.ptr(out), L.ptr(phiinv), L.ptr(m0), L.ptr(mommask), ws.N,
+                                          ws.d, ws.sh, float(dt), alpha, beta, gamma, L.ptr(ws.buf), ws.nbytes,
+                                          L.stream_ptr(ws.dev)))
+    return out
+
+
+def _fusable(metric, m0, phiinv, mommask):
+    if not isinstance(metric, FluidMetric) or _needs_grad(m0, phiinv, mommask):
+        return False
+    if not (m0.is_cuda and phiinv.is_cuda and m0.shape == phiinv.shape and m0.dtype == phiinv.dtype):
+        return False
+    return mommask is None or (mommask.shape == m0.shape and mommask.dtype == m0.dtype and mommask.is_cuda)
+
+
+def EPDiff_step(metric, m0, dt, phiinv, mommask=None):
+    """phiinv <- -dt*v + phiinv(x - dt*v), v = sharp(Ad_star(phiinv, m0)) (lddmm.py:39-44).
+
+    Without autograd this is one library call (three fused stages); with autograd it is
+    the same three stages as differentiable Functions."""
+    if _fusable(metric, m0, phiinv, mommask):
+        m0c, pc = L.aligned(m0), L.aligned(phiinv)
+        mk = None if mommask is None else mommask.contiguous()
+        return _fused_step(metric, m0c, dt, pc, mk, _StepWorkspace(m0c), torch.empty_like(pc))
+    m = adjrep.Ad_star(phiinv, m0)
+    if mommask is not None:
+        m = m * mommask
+    v = metric.sharp(m)
+    return deform.compose_disp_vel(phiinv, v, dt=-dt)
+
+
+EPDiffStep = EPDiff_step  # alias used by the project brief
+
+
+class EPDiffStepsFunction(torch.autograd.Function):
+    """N EPDiff steps with activation recomputation: only (m0, phiinv) are kept and the block is
+    replayed in backward. (The reference's version, lddmm.py:47-70, has swapped arguments and is
+    unreachable; this is the working equivalent.)"""
+
+    @staticmethod
+    def forward(ctx, metric, m0, dt, N, phiinv, mommask):
+        ctx.metric, ctx.dt, ctx.N, ctx.mommask = metric, dt, N, mommask
+        ctx.save_for_backward(m0, phiinv)
+        with torch.no_grad():
+            for n in range(N):
+                phiinv = EPDiff_step(metric, m0, dt, phiinv, mommask=mommask)
+        return phiinv
+
+    @staticmethod
+    def backward(ctx, gradout):
+        m0, phiinv = ctx.saved_tensors
+        with torch.enable_grad():
+            m0_ = m0.detach().requires_grad_(ctx.needs_input_grad[1])
+            p_ = phiinv.detach().requires_grad_(ctx.needs_input_grad[4])
+            p = p_
+            for n in range(ctx.N):
+                p = EPDiff_step(ctx.metric, m0_, ctx.dt, p, mommask=ctx.mommask)
+            inputs = [t for t in (m0_, p_) if t.requires_grad]
+            grads = list(torch.autograd.grad(p, inputs, gradout)) if inputs else []
+        g_m0 = grads.pop(0) if m0_.requires_grad else None
+        g_p = grads.pop(0) if p_.requires_grad else None
+        return None, g_m0, None, None, g_p, None
+
+
+def EPDiff_steps(metric, m0, dt, N, phiinv, mommask=None):
+    return EPDiffStepsFunction.apply(metric, m0, dt, N, phiinv, mommask)
+
+
+def expmap(metric, m0, T=1.0, num_steps=10, phiinv=None, mommask=None, checkpoints=False):
+    """Exponential map of an initial momentum; returns the displacement of phi^{-1}
+    (reference: lddmm.py:73-105; the non-checkpointed branch :87-91 is the parity target).
+
+    checkpoints: False/None -> plain loop; int k -> recompute in blocks of k steps;
+    True -> blocks of ~sqrt(num_steps) steps (num_steps unchanged, last block shorter)."""
+    if phiinv is None:
+        phiinv = torch.zeros_like(m0)
+    dt = T / num_steps
+    if checkpoints is None or checkpoints is False:
+        if _fusable(metric, m0, phiinv, mommask) and num_steps > 0:
+            m0c, cur = L.aligned(m0), L.aligned(phiinv)
+            mk = None if mommask is None else mommask.contiguous()
+            ws = _StepWorkspace(m0c)
+            bufs = [torch.empty_like(cur), torch.empty_like(cur)]
+            for i in range(num_steps):
+                cur = _fused_step(metric, m0c, dt, cur, mk, ws, bufs[i % 2])
+            return cur
+        for i in range(num_steps):
+            phiinv = EPDiff_step(metric, m0, dt, phiinv, mommask=mommask)
+        return phiinv
+    cps = int(math.sqrt(num_steps)) if checkpoints is True else int(checkpoints)
+    cps = max(1, cps)
+    done = 0
+    while done < num_steps:
+        k = min(cps, num_steps - done)
+        if _needs_grad(m0, phiinv):
+            phiinv = EPDiff_steps(metric, m0, dt, k, phiinv, mommask)
+        else:
+            for i in range(k):
+                phiinv = EPDiff_step(metric, m0, dt, phiinv, mommask=mommask)
+        done += k
+    return phiinv

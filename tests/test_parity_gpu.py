@@ -1,0 +1,233 @@
+"""Parity of the CUDA product (through the Python mirror -> C ABI) against the CPU oracle,
+on the same seeded inputs. fp64 to 1e-12, fp32 to 1e-5 relative (splat 1e-4: atomic order)."""
+import pytest
+import torch
+
+import util
+from util import randn, relerr, l2err, smooth_field, tol_for
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.float64]
+SHAPES = {2: [(7, 9), (32, 16)], 3: [(5, 6, 7), (16, 8, 32)]}
+
+
+def cases():
+    for dim in (2, 3):
+        for sh in SHAPES[dim]:
+            for dt in DTYPES:
+                yield dim, sh, dt
+
+
+def disp_like(N, dim, sh, dtype, seed, amp=2.5):
+    """displacement with out-of-range excursions at the border (clamp path)"""
+    u = randn((N, dim) + sh, dtype, seed, scale=amp)
+    u[:, :, 0] -= 3.0
+    u[..., -1] += 3.5
+    return u
+
+
+@pytest.mark.parametrize("dim,sh,dtype", list(cases()))
+@pytest.mark.parametrize("bcast", [False, True])
+@pytest.mark.parametrize("C", [1, 3])
+def test_interp_forward(lm, orc, dim, sh, dtype, bcast, C):
+    N = 3
+    I = randn((1 if bcast else N, C) + sh, dtype, 11)
+    u = disp_like(N, dim, sh, dtype, 12)
+    for dt in (1.0, -0.1):
+        ref = orc.interp(I, u, dt)
+        out = lm.interp(I.cuda(), u.cuda(), dt)
+        assert relerr(out, ref) <= tol_for(dtype)
+
+
+@pytest.mark.parametrize("dim,sh,dtype", list(cases()))
+@pytest.mark.parametrize("bcast", [False, True])
+def test_interp_backward(lm, orc, dim, sh, dtype, bcast):
+    N, C = 2, 2
+    I = randn((1 if bcast else N, C) + sh, dtype, 21)
+    u = disp_like(N, dim, sh, dtype, 22)
+    go = randn((N, C) + sh, dtype, 23)
+    dI_ref, du_ref = orc.interp_backward(go, I, u, 0.7)
+    Ic, uc = I.cuda().requires_grad_(True), u.cuda().requires_grad_(True)
+    out = lm.interp(Ic, uc, 0.7)
+    dI, du = torch.autograd.grad(out, [Ic, uc], go.cuda())
+    assert relerr(du, du_ref) <= tol_for(dtype)
+    assert relerr(dI, dI_ref) <= tol_for(dtype, splat=True)
+    # splat conserves mass: sum d_I == sum gout (clamp keeps everything inside)
+    assert abs(dI.double().sum().item() - go.double().sum().item()) <= 1e-5 * go.double().abs().sum().item()
+    # interp_adjoint == d_I
+    adj = lm.interp_adjoint(go.cuda(), u.cuda(), 0.7, broadcast=bcast)
+    assert relerr(adj, dI_ref) <= tol_for(dtype, splat=True)
+
+
+@pytest.mark.parametrize("dim,sh,dtype", list(cases()))
+@pytest.mark.parametrize("disp", [False, True])
+@pytest.mark.parametrize("trans", [False, True])
+def test_jtvf_forward_backward(lm, orc, dim, sh, dtype, disp, trans):
+    N = 2
+    v = randn((N, dim) + sh, dtype, 31)
+    w = randn((N, dim) + sh, dtype, 32)
+    go = randn((N, dim) + sh, dtype, 33)
+    ref = orc.jtvf_forward(v, w, disp, trans)
+    dv_ref, dw_ref = orc.jtvf_backward(go, v, w, disp, trans)
+    vc, wc = v.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    out = lm.jacobian_times_vectorfield(vc, wc, displacement=disp, transpose=trans)
+    assert relerr(out, ref) <= tol_for(dtype)
+    dv, dw = torch.autograd.grad(out, [vc, wc], go.cuda())
+    assert relerr(dv, dv_ref) <= tol_for(dtype)
+    assert relerr(dw, dw_ref) <= tol_for(dtype)
+
+
+@pytest.mark.parametrize("dim,sh,dtype", list(cases()))
+def test_jtvf_scalar_channels(lm, orc, dim, sh, dtype):
+    """non-transposed, non-displacement mode accepts any channel count for v"""
+    N, C = 2, 4
+    v = randn((N, C) + sh, dtype, 34)
+    w = randn((N, dim) + sh, dtype, 35)
+    ref = orc.jtvf_forward(v, w, False, False)
+    out = lm.jacobian_times_vectorfield(v.cuda(), w.cuda(), displacement=False, transpose=False)
+    assert relerr(out, ref) <= tol_for(dtype)
+
+
+@pytest.mark.parametrize("dim,sh,dtype", list(cases()))
+def test_jtvf_adjoint_forward_backward(lm, orc, dim, sh, dtype):
+    N = 2
+    z = randn((N, dim) + sh, dtype, 41)
+    w = randn((N, dim) + sh, dtype, 42)
+    go = randn((N, dim) + sh, dtype, 43)
+    ref = orc.jtvf_adjoint_forward(z, w)
+    dz_ref, dw_ref = orc.jtvf_adjoint_backward(go, z, w)
+    zc, wc = z.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    out = lm.jacobian_times_vectorfield_adjoint(zc, wc)
+    assert relerr(out, ref) <= tol_for(dtype)
+    dz, dw = torch.autograd.grad(out, [zc, wc], go.cuda())
+    assert relerr(dz, dz_ref) <= tol_for(dtype)
+    assert relerr(dw, dw_ref) <= tol_for(dtype)
+
+
+@pytest.mark.parametrize("dim,sh,dtype", list(cases()))
+def test_fused_adjrep(lm, orc, dim, sh, dtype):
+    N = 2
+    v = randn((N, dim) + sh, dtype, 51)
+    m = randn((N, dim) + sh, dtype, 52)
+    phi = disp_like(N, dim, sh, dtype, 53, amp=1.5)
+    assert relerr(lm.ad(v.cuda(), m.cuda()), orc.ad(v, m)) <= tol_for(dtype)
+    assert relerr(lm.ad_star(v.cuda(), m.cuda()), orc.ad_star(v, m)) <= tol_for(dtype)
+    assert relerr(lm.Ad_star(phi.cuda(), m.cuda()), orc.Ad_star(phi, m)) <= tol_for(dtype)
+    for ds, dt in ((1.0, 1.0), (-0.1, 1.0), (0.3, -2.0)):
+        assert relerr(lm.compose(phi.cuda(), v.cuda(), ds, dt), orc.compose(phi, v, ds, dt)) <= tol_for(dtype)
+
+
+FLUID_SHAPES = {2: [(3, 3), (6, 10), (16, 32), (64, 64)], 3: [(3, 3, 3), (4, 6, 5), (8, 16, 32), (32, 8, 16)]}
+FLUID_PARAMS = [[0.1, 0.0, 0.01], [0.1, 0.01, 0.001], [1.0, 0.1, 0.01]]
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("params", FLUID_PARAMS)
+def test_fluid_metric(lm, orc, dim, dtype, params):
+    for sh in FLUID_SHAPES[dim]:
+        m = randn((2, dim) + sh, dtype, 61)
+        om, gm = orc.FluidMetric(params), lm.FluidMetric(params)
+        tol = 1e-5 if dtype == torch.float32 else 1e-11
+        assert l2err(gm.sharp(m.cuda()), om.sharp(m)) <= tol, (sh, "sharp")
+        assert l2err(gm.flat(m.cuda()), om.flat(m)) <= tol, (sh, "flat")
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("params", FLUID_PARAMS)
+@pytest.mark.parametrize("inverse", [True, False])
+def test_fluid_operator_boundary(lm, orc, dim, dtype, params, inverse):
+    """the standalone multiplier (reference FFI fluid_operator) on a torch.fft spectrum"""
+    sh = (6, 5) if dim == 2 else (4, 6, 5)
+    m = randn((2, dim) + sh, dtype, 62)
+    dims = tuple(range(2, 2 + dim))
+    F = torch.view_as_real(torch.fft.rfftn(m, dim=dims, norm="ortho")).contiguous()
+    cos, sin = orc.FluidMetric.luts(m.shape, dtype)
+    Fg = F.cuda()
+    lm.fluid_operator(Fg, inverse, [c.cuda() for c in cos], [s.cuda() for s in sin], *params)
+    orc.fluid_operator(F, inverse, cos, sin, *params)
+    assert relerr(Fg, F) <= (1e-5 if dtype == torch.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("dim,sh", [(2, (32, 32)), (3, (16, 16, 16))])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("steps", [1, 5])
+def test_expmap(lm, orc, dim, sh, dtype, steps):
+    params = [0.1, 0.0, 0.01]
+    N = 2
+    om, gm = orc.FluidMetric(params), lm.FluidMetric(params)
+    m0 = smooth_field((N, dim) + sh, torch.float64, 71, amp=1.0, sigma=2.0)
+    v0 = om.sharp(m0)
+    m0 = (m0 * (3.0 / v0.abs().max())).to(dtype)  # max |v| = 3 voxels
+    ref = orc.expmap(om, m0, num_steps=steps)
+    out = lm.expmap(gm, m0.cuda(), num_steps=steps)
+    tol = 1e-4 if dtype == torch.float32 else 1e-10
+    assert relerr(out, ref) <= tol
+    # the autograd (unfused) path computes the same thing
+    out2 = lm.expmap(gm, m0.cuda().requires_grad_(True), num_steps=steps)
+    assert relerr(out2, ref) <= tol
+    # expmap_advect
+    ref3 = orc.expmap_advect(om, m0, num_steps=steps)
+    out3 = lm.expmap_advect(gm, m0.cuda(), num_steps=steps)
+    assert relerr(out3, ref3) <= tol
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("disp", [False, True])
+def test_regrid(lm, orc, dim, dtype, disp):
+    sh = (9, 7) if dim == 2 else (6, 9, 7)
+    osh = (13, 12) if dim == 2 else (11, 13, 12)
+    I = randn((2, dim) + sh, dtype, 81)
+    ref = orc.regrid(I, osh, displacement=disp)
+    Ic = I.cuda().requires_grad_(True)
+    out = lm.regrid(Ic, shape=osh, displacement=disp)
+    assert relerr(out, ref) <= tol_for(dtype)
+    go = randn(tuple(out.shape), dtype, 82)
+    (dI,) = torch.autograd.grad(out, [Ic], go.cuda())
+    origin = tuple((s - 1) * 0.5 for s in sh)
+    spacing = tuple((a - 1) / (b - 1) for a, b in zip(sh, osh))
+    gs = go
+    if disp:
+        gs = go * (1.0 / torch.tensor(spacing, dtype=dtype).view(1, dim, *[1] * dim))
+    dI_ref = orc.regrid_backward(gs, sh, osh, origin, spacing)
+    assert relerr(dI, dI_ref) <= tol_for(dtype, splat=True)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("bcast", [False, True])
+def test_affine_interp_forward(lm, orc, dim, dtype, bcast):
+    sh = (9, 7) if dim == 2 else (6, 9, 7)
+    N, C = 3, 2
+    I = randn((1 if bcast else N, C) + sh, dtype, 91)
+    A = torch.eye(dim, dtype=dtype).repeat(N, 1, 1) + randn((N, dim, dim), dtype, 92, 0.1)
+    T = randn((N, dim), dtype, 93, 1.5)
+    ref = orc.affine_interp_forward(I, A, T)
+    out = lm.affine_interp(I.cuda(), A.cuda(), T.cuda())
+    # coordinates are a 3-term fp32 dot product whose contraction order differs between
+    # compilers: allow one coordinate ulp times the image gradient
+    assert relerr(out, ref) <= (5e-5 if dtype == torch.float32 else 1e-12)
+
+
+def test_empty_and_errors(lm):
+    z = torch.zeros(0, 3, 4, 4, 4, device="cuda")
+    assert lm.interp(z, z).shape == z.shape
+    assert lm.jacobian_times_vectorfield(z, z).shape == z.shape
+    with pytest.raises(RuntimeError):
+        lm.interp(torch.zeros(1, 1, 4, 4), torch.zeros(1, 2, 4, 4))  # CPU tensors: no fallback
+    with pytest.raises(RuntimeError):
+        lm.jacobian_times_vectorfield(torch.zeros(1, 3, 4, 4, 1).cuda(), torch.zeros(1, 3, 4, 4, 1).cuda())  # thin
+    with pytest.raises(RuntimeError):
+        lm.interp(torch.zeros(2, 1, 4, 4).cuda(), torch.zeros(3, 2, 4, 4).cuda())  # batch mismatch
+
+
+def test_debug_mode_and_launch_count(lm):
+    lm.set_debug_mode(True)
+    n0 = lm.launch_count()
+    x = torch.randn(1, 2, 8, 8, device="cuda")
+    lm.interp(x, x)
+    assert lm.launch_count() == n0 + 1
+    lm.set_debug_mode(False)
