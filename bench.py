@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- EPDiff-shoot throughput (3-D voxel-steps/s) on N B200s of one node.
+
+One bench "step" = one forward geodesic shoot (`expmap`, num_steps EPDiff steps) of one batch of
+synthetic momenta per GPU. Default workload is BASELINE.json configs[1] (C2: 3-D 128^3, batch 16,
+10 steps); `--workload c3` is the per-GPU share of configs[2] (256^3, batch 8, 5 steps).
+
+  value  : whole-job voxel-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e    : the same through the public API with HOST buffers: pinned-host momenta -> device, shoot,
+           deformation -> pinned host, all inside the timed region
+  roofline: dominant kernel of the step, timed live with CUDA events on the launch stream
+  cpu_baseline: the CPU oracle (port of the reference; the reference has no CPU path for this,
+           SURVEY.md F1) on a bounded sample, rank 0 / N=1 only
+
+`--impl reference` times that CPU port alone (all host threads) on the same metric/config.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (batch per GPU, (X,Y,Z), EPDiff steps per shoot)
+    "c2": (16, (128, 128, 128), 10),
+    "c3": (8, (256, 256, 256), 5),
+    "tiny": (2, (32, 32, 32), 3),
+}
+PARAMS = [0.1, 0.0, 0.01]           # FluidMetric used by the atlas builder (lddmm.py:213)
+ALG_BYTES_PER_VOXEL_STEP = 96       # Ad*(36) + sharp(24) + compose(36), fp32 3-D
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_momenta(N, shape, seed, device=None, scale_to=4.0):
+    """White noise low-passed by the metric itself, scaled so that max|sharp(m0)| = 4 voxels
+    (BASELINE.md section 4). Generated on the CPU (seeded), deterministic per rank."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    m = torch.randn((N, 3) + tuple(shape), generator=g, dtype=torch.float32)
+    return m
+
+
+class ClockSampler:
+    """nvidia-smi SM clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_throughput(shape, batch, steps, reps=1):
+    """voxel-steps/s of the CPU oracle (OpenMP kernels + torch.fft/MKL) on a bounded sample."""
+    import torch
+    from oracle import oracle as orc
+    orc.lib()
+    met = orc.FluidMetric(PARAMS)
+    m0 = make_momenta(batch, shape, 1)
+    m0 = m0 * (4.0 / met.sharp(m0).abs().max())
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.expmap(met, m0, num_steps=steps)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    V = shape[0] * shape[1] * shape[2]
+    return batch * V * steps / best, best
+
+
+def run_reference(args):
+    """The reference arm: the CPU port of the reference path, all host threads, same metric."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch, shape, nsteps = WORKLOADS[args.workload]
+    sample_batch = 1
+    V = shape[0] * shape[1] * shape[2]
+    from oracle import oracle as orc
+    orc.lib()
+    met = orc.FluidMetric(PARAMS)
+    m0 = make_momenta(sample_batch, shape, 1)
+    m0 = m0 * (4.0 / met.sharp(m0).abs().max())
+    for _ in range(args.warmup):
+        orc.expmap(met, m0, num_steps=1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.expmap(met, m0, num_steps=nsteps)
+    dt = time.perf_counter() - t0
+    val = sample_batch * V * nsteps * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = "%d subject(s) of %dx%dx%d, %d EPDiff steps per bench step" % ((sample_batch,) + tuple(shape) + (nsteps,))
+    line = {
+        "impl": "reference", "metric": "3D voxel-steps/sec (EPDiff shoot)", "value": val, "unit": "voxel-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "shape": list(shape), "batch_per_gpu": batch, "epdiff_steps": nsteps,
+                   "metric_params": PARAMS, "note": "CPU port of the reference path (oracle/): the reference has no CPU "
+                   "implementation of interp/jacobian/fluid kernels (SURVEY.md F1) and does not build on torch 2.x (F2)"},
+        "cpu_baseline": {"value": val, "unit": "voxel-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "voxel-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary 256^3 measurement")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import lagomorph_b200 as lm
+    from lagomorph_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    metric = lm.FluidMetric(PARAMS)
+
+    def measure(workload, K, W, with_e2e=True):
+        batch, shape, nsteps = WORKLOADS[workload]
+        V = shape[0] * shape[1] * shape[2]
+        m_host = make_momenta(batch, shape, 1 + rank).pin_memory()
+        m0 = m_host.to(dev, non_blocking=True)
+        torch.cuda.synchronize()
+        # scale so the flow moves ~4 voxels (diffeomorphic, realistic gather locality)
+        v0max = metric.sharp(m0).abs().max().item()
+        m0.mul_(4.0 / v0max)
+        m_host.mul_(4.0 / v0max)
+        shoot = lambda: lm.expmap(metric, m0, num_steps=nsteps)
+        for _ in range(W):
+            h = shoot()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        n0 = lm.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(K):
+            h = shoot()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        launches = lm.launch_count() - n0
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        value = world * batch * V * nsteps * K / (ms * 1e-3)
+        res = {"value": value, "ms_per_step": ms / K, "launches": launches, "clocks": clocks,
+               "batch": batch, "shape": shape, "nsteps": nsteps, "V": V}
+        # ---- per-kernel breakdown (profile mode: an event after every library launch) ----
+        buf = ctypes.create_string_buffer(1 << 16)
+        torch.cuda.synchronize()
+        L.check(L.lib.lgm_profile_begin(L.stream_ptr(dev)))
+        for _ in range(max(1, K // 2)):
+            shoot()
+        L.check(L.lib.lgm_profile_end(buf, len(buf)))
+        res["kernels"] = json.loads(buf.value.decode())
+        res["kernel_reps"] = max(1, K // 2)
+        # ---- end to end through the public API with host buffers ----
+        if with_e2e:
+            h_host = torch.empty((batch, 3) + tuple(shape), dtype=torch.float32).pin_memory()
+            def e2e_step():
+                md = m_host.to(dev, non_blocking=True)
+                hh = lm.expmap(metric, md, num_steps=nsteps)
+                h_host.copy_(hh, non_blocking=True)
+            for _ in range(min(W, 2)):
+                e2e_step()
+            barrier()
+            e0.record()
+            for _ in range(K):
+                e2e_step()
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res["e2e"] = {"value": world * batch * V * nsteps * K / (t.item() * 1e-3), "unit": "voxel-steps/s",
+                          "h2d_bytes_per_step": m_host.numel() * 4, "d2h_bytes_per_step": h_host.numel() * 4}
+        del m0, h
+        torch.cuda.empty_cache()
+        return res
+
+    # algorithmic bytes per voxel of the launch, fp32 3-D (DESIGN.md "Kernels")
+    def alg_bytes(name, shape):
+        zc = shape[2] // 2 + 1
+        spec = 3 * 8.0 * zc / shape[2]          # one pass over the 3-channel half spectrum, per voxel
+        return {"Ad_star": 36.0, "compose": 36.0, "zfwd": 12.0 + spec, "zinv": 12.0 + spec,
+                "ypass": 2 * spec, "xpass": 2 * spec, "slab_fwd": 12.0 + spec, "slab_inv": 12.0 + spec}.get(name)
+
+    main_res = measure(args.workload, args.steps, args.warmup)
+    hbm, peak_src = peaks()
+    batch, shape, nsteps, V = main_res["batch"], main_res["shape"], main_res["nsteps"], main_res["V"]
+    ks = main_res["kernels"]
+    dom = max(ks, key=lambda k: ks[k]["ms"]) if ks else None
+    roofline = None
+    breakdown = {}
+    for k, v in ks.items():
+        per_launch_ms = v["ms"] / v["launches"]
+        ab = alg_bytes(k, shape)
+        entry = {"launches_per_shoot": v["launches"] // main_res["kernel_reps"], "ms_per_launch": per_launch_ms,
+                 "share": v["ms"] / sum(x["ms"] for x in ks.values())}
+        if ab is not None:
+            # every launch of these kernels covers the whole batch once
+            entry["achieved_gbs"] = ab * batch * V / (per_launch_ms * 1e-3) / 1e9
+            entry["frac"] = entry["achieved_gbs"] / hbm
+        breakdown[k] = entry
+    if dom is not None and "achieved_gbs" in breakdown[dom]:
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": breakdown[dom]["achieved_gbs"], "peak": hbm,
+                    "unit": "GB/s", "frac": breakdown[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_voxel": alg_bytes(dom, shape)}
+    step_frac = main_res["value"] / world * ALG_BYTES_PER_VOXEL_STEP / 1e9 / hbm
+
+    extra = None
+    if not args.no_extra and args.workload == "c2":
+        try:
+            r3 = measure("c3", max(2, args.steps // 2), 2, with_e2e=False)
+            extra = {"c3_256": {"value": r3["value"], "unit": "voxel-steps/s", "ms_per_step": r3["ms_per_step"],
+                                "hbm_roofline_frac_96B": r3["value"] / world * ALG_BYTES_PER_VOXEL_STEP / 1e9 / hbm,
+                                "config": {"shape": list(r3["shape"]), "batch_per_gpu": r3["batch"], "epdiff_steps": r3["nsteps"]}}}
+        except Exception as e:  # never lose the main line
+            extra = {"c3_256": {"error": str(e)[:200]}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, secs = cpu_port_throughput(shape, 2, nsteps)
+        cpu = {"value": val, "unit": "voxel-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "2 subjects of %dx%dx%d, %d EPDiff steps (%.1f s)" % (tuple(shape) + (nsteps, secs))}
+
+    if rank == 0:
+        line = {
+            "metric": "3D voxel-steps/sec (EPDiff shoot)", "value": main_res["value"], "unit": "voxel-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "shape": list(shape), "batch_per_gpu": batch,
+                       "epdiff_steps": nsteps, "metric_params": PARAMS,
+                       "l2": "inputs larger than L2 (%d MiB per field vs 126 MB)" % (batch * 3 * V * 4 >> 20),
+                       "parallelism": "subjects sharded over ranks, no data-path collective"},
+            "hbm_roofline_frac_96B": step_frac,
+            "roofline": roofline, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
+            "e2e": main_res.get("e2e"), "gpu_launches": main_res["launches"], "clocks": main_res["clocks"],
+        }
+        if extra:
+            line["also"] = extra
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

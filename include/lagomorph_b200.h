@@ -45,6 +45,12 @@ int lgm_get_debug_mode(void);
 /* number of kernel launches issued by this library since process start */
 int64_t lgm_launch_count(void);
 
+/* Bench-only profiling: between begin and end an event is recorded after every kernel this
+ * library launches on `stream`; end() synchronises and writes a JSON object
+ * {"kernel": {"launches": n, "ms": total}} (time of a launch = gap to the previous event). */
+int lgm_profile_begin(void* stream);
+int lgm_profile_end(char* json, int64_t json_bytes);
+
 /* interp --------------------------------------------------------------------
  * replaces interp_forward (extension.cpp:135-143 -> cuda/interp.cu:80-130):
  *   out[n,c,x] = lerp_clamp(I[n or 0, c], x + dt*u[n,:,x]);  I broadcasts iff NI < N.

@@ -27,6 +27,8 @@ SIGNATURES = {
     "lgm_set_debug_mode": (None, [c_int]),
     "lgm_get_debug_mode": (c_int, []),
     "lgm_launch_count": (c_i64, []),
+    "lgm_profile_begin": (c_int, [c_void_p]),
+    "lgm_profile_end": (c_int, [ctypes.c_char_p, c_i64]),
     "lgm_interp_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_i64_p, c_double, c_void_p]),
     "lgm_interp_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_i64_p, c_double, c_void_p]),
     "lgm_jtvf_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_int, c_i64_p, c_int, c_int, c_void_p]),

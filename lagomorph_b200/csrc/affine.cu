@@ -182,7 +182,7 @@ static int affine_fwd_t(void* out, const void* I, const void* A, const void* T, 
   dim3 grid((unsigned)cdiv(g.V, kThreads), (unsigned)N);
   const long long ibs = (NI == 1 && N > 1) ? 0 : C * g.V;
   affine_fwd_kernel<R, D><<<grid, kThreads, 0, s>>>((R*)out, (const R*)I, (const R*)A, (const R*)T, g, (int)C, ibs);
-  count_launch();
+  count_launch("affine_fwd", s);
   return finish(s, "lgm_affine_interp_fwd");
 }
 
@@ -205,7 +205,7 @@ static int affine_bwd_t(void* d_I, void* d_A, void* d_T, const void* go, const v
   else if (d_I) L(true, false);
   else L(false, true);
 #undef L
-  count_launch();
+  count_launch("affine_bwd", s);
   return finish(s, "lgm_affine_interp_bwd");
 }
 

@@ -9,7 +9,7 @@ namespace lgm {
 // ---- host-side error plumbing (capi.cu) --------------------------------------
 int set_error(int code, const char* fmt, ...);
 int finish(cudaStream_t s, const char* what);  // checks launch error (+sync in debug mode)
-void count_launch(int n = 1);
+void count_launch(const char* name, cudaStream_t s);  // counts; in profile mode also timestamps
 bool debug_mode();
 
 #define LGM_REQUIRE(cond, ...)                                   \

@@ -357,7 +357,7 @@ static int jtvf_fwd_t(void* out, const void* v, const void* w, int64_t N, int64_
   else if (trans) L(false, true);
   else L(false, false);
 #undef L
-  count_launch();
+  count_launch("jtvf_fwd", s);
   return finish(s, "lgm_jtvf_fwd");
 }
 
@@ -384,7 +384,7 @@ static int jtvf_bwd_t(void* d_v, void* d_w, const void* go, const void* v, const
   else if (disp) jtvf_bwd_launch<R, D, true, false>(grid, s, d_v, d_w, go, v, w, g, (int)C);
   else if (trans) jtvf_bwd_launch<R, D, false, true>(grid, s, d_v, d_w, go, v, w, g, (int)C);
   else jtvf_bwd_launch<R, D, false, false>(grid, s, d_v, d_w, go, v, w, g, (int)C);
-  count_launch();
+  count_launch("jtvf_bwd", s);
   return finish(s, "lgm_jtvf_bwd");
 }
 
@@ -396,7 +396,7 @@ static int jtvf_adj_fwd_t(void* out, const void* z, const void* w, int64_t N, in
   if (N == 0 || C == 0) return LGM_OK;
   dim3 grid((unsigned)cdiv(g.V, kThreads), (unsigned)N);
   jtvf_adj_fwd_kernel<R, D><<<grid, kThreads, 0, s>>>((R*)out, (const R*)z, (const R*)w, g, (int)C);
-  count_launch();
+  count_launch("jtvf_adj_fwd", s);
   return finish(s, "lgm_jtvf_adj_fwd");
 }
 
@@ -413,7 +413,7 @@ static int jtvf_adj_bwd_t(void* d_z, void* d_w, const void* go, const void* z, c
   else if (d_z) L(true, false);
   else L(false, true);
 #undef L
-  count_launch();
+  count_launch("jtvf_adj_bwd", s);
   return finish(s, "lgm_jtvf_adj_bwd");
 }
 
@@ -425,7 +425,7 @@ static int ad_t(void* out, const void* v, const void* m, int64_t N, const int64_
   if (N == 0) return LGM_OK;
   dim3 grid((unsigned)cdiv(g.V, kThreads), (unsigned)N);
   ad_kernel<R, D, STAR><<<grid, kThreads, 0, s>>>((R*)out, (const R*)v, (const R*)m, g);
-  count_launch();
+  count_launch("ad", s);
   return finish(s, STAR ? "lgm_ad_star_fwd" : "lgm_ad_fwd");
 }
 template <typename R, int D>
@@ -445,7 +445,7 @@ int Ad_star_generic(void* out, const void* phi, const void* m, int64_t N, const 
   if (N == 0) return LGM_OK;
   dim3 grid((unsigned)cdiv(g.V, kThreads), (unsigned)N);
   Ad_star_kernel<R, D><<<grid, kThreads, 0, s>>>((R*)out, (const R*)phi, (const R*)m, g);
-  count_launch();
+  count_launch("Ad_star", s);
   return finish(s, "lgm_Ad_star_fwd");
 }
 
@@ -456,7 +456,7 @@ int compose_generic(void* out, const void* u, const void* v, int64_t N, const in
   if (N == 0 || g.V == 0) return LGM_OK;
   dim3 grid((unsigned)cdiv(g.V, kThreads), (unsigned)N);
   compose_kernel<R, D><<<grid, kThreads, 0, s>>>((R*)out, (const R*)u, (const R*)v, g, ds, dt);
-  count_launch();
+  count_launch("compose", s);
   return finish(s, "lgm_compose_fwd");
 }
 

@@ -53,7 +53,7 @@ extern "C" int lgm_epdiff_step_fwd(int dtype, void* phiinv_out, const void* phii
       mul_mask_kernel<float><<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((float*)m, (const float*)mommask, total, total);
     else
       mul_mask_kernel<double><<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((double*)m, (const double*)mommask, total, total);
-    count_launch();
+    count_launch("mul_mask", (cudaStream_t)stream);
   }
   rc = lgm_fluid_apply(dtype, m, m, N, dim, shape, 1, alpha, beta, gamma, ws, scratch_bytes - (int64_t)field, stream);
   if (rc) return rc;

@@ -608,7 +608,7 @@ struct FastLaunch {
     const size_t smem = sizeof(C) * ((size_t)(M + 1) * (ZL + 1) + Z + M);
     LGM_CUDA_TRY(set_smem(zfwd_kernel<R, Z, ZL>, smem), "zfwd smem");
     zfwd_kernel<R, Z, ZL><<<(unsigned)cdiv(rows, ZL), kFftThreads, smem, s>>>(spec, in, rows, tw);
-    count_launch();
+    count_launch("zfwd", s);
     return LGM_OK;
   }
   template <int Z>
@@ -617,7 +617,7 @@ struct FastLaunch {
     const size_t smem = sizeof(C) * ((size_t)(M + 1) * (ZL + 1) + Z + M);
     LGM_CUDA_TRY(set_smem(zinv_kernel<R, Z, ZL>, smem), "zinv smem");
     zinv_kernel<R, Z, ZL><<<(unsigned)cdiv(rows, ZL), kFftThreads, smem, s>>>(out, spec, rows, tw);
-    count_launch();
+    count_launch("zinv", s);
     return LGM_OK;
   }
   template <int NY, bool INV>
@@ -626,7 +626,7 @@ struct FastLaunch {
     LGM_CUDA_TRY(set_smem(ypass_kernel<R, NY, T, INV>, smem), "ypass smem");
     dim3 grid((unsigned)cdiv(Zc, T), (unsigned)X, (unsigned)NC);
     ypass_kernel<R, NY, T, INV><<<grid, kFftThreads, smem, s>>>(spec, X, Zc, tw);
-    count_launch();
+    count_launch("ypass", s);
     return LGM_OK;
   }
   template <int NX, int D, int NCH, bool INVERSE>
@@ -638,7 +638,7 @@ struct FastLaunch {
     xpass_kernel<R, NX, T, D, NCH, INVERSE><<<grid, kFftThreads, smem, s>>>(
         spec, plane, Zc, (const C*)p.tw[0], (const R*)p.wl[0], (const R*)p.sl[0], (const R*)p.wl[1],
         (const R*)p.sl[1], (const R*)p.wl[2], (const R*)p.sl[2], alpha, beta, gamma, scale);
-    count_launch();
+    count_launch("xpass", s);
     return LGM_OK;
   }
   template <int NX, int D>
@@ -724,7 +724,7 @@ static void launch_operator(R* Fm, int inverse, const FluidPlan& p, double alpha
     fluid_operator_kernel<R, D, true><<<blocks, 256, 0, s>>>(Fm, (const R*)p.wl[0], (const R*)p.sl[0], (const R*)p.wl[1], (const R*)p.sl[1], (const R*)p.wl[2], (const R*)p.sl[2], alpha, beta, gamma, N, g);
   else
     fluid_operator_kernel<R, D, false><<<blocks, 256, 0, s>>>(Fm, (const R*)p.wl[0], (const R*)p.sl[0], (const R*)p.wl[1], (const R*)p.sl[1], (const R*)p.wl[2], (const R*)p.sl[2], alpha, beta, gamma, N, g);
-  count_launch();
+  count_launch("fluid_operator", s);
 }
 
 template <typename R>
@@ -742,14 +742,14 @@ static int fluid_naive(void* out, const void* in, int64_t N, int dim, const int6
   const R sc = (R)(1.0 / sqrt((double)V));
   const int th = 256;
   dft_r2c_kernel<R><<<(unsigned)cdiv(S, th), th, 0, s>>>(A, (const R*)in, lines, nlast, nc, (const C*)p.tw[dim - 1], sc);
-  count_launch();
+  count_launch("dft_r2c", s);
   C* cur = A;
   C* oth = B;
   // remaining axes from the second-to-last to the first
   long long st = nc;
   for (int a = dim - 2; a >= 0; --a) {
     dft_c2c_kernel<R, false><<<(unsigned)cdiv(S, th), th, 0, s>>>(oth, cur, S, (int)shape[a], st, (const C*)p.tw[a], R(1));
-    count_launch();
+    count_launch("dft_c2c", s);
     C* t = cur; cur = oth; oth = t;
     st *= shape[a];
   }
@@ -761,12 +761,12 @@ static int fluid_naive(void* out, const void* in, int64_t N, int dim, const int6
   st = nc;
   for (int a = dim - 2; a >= 0; --a) {
     dft_c2c_kernel<R, true><<<(unsigned)cdiv(S, th), th, 0, s>>>(oth, cur, S, (int)shape[a], st, (const C*)p.tw[a], R(1));
-    count_launch();
+    count_launch("dft_c2c", s);
     C* t = cur; cur = oth; oth = t;
     st *= shape[a];
   }
   dft_c2r_kernel<R><<<(unsigned)cdiv(lines * nlast, th), th, 0, s>>>((R*)out, cur, lines, nlast, nc, (const C*)p.tw[dim - 1], sc);
-  count_launch();
+  count_launch("dft_c2r", s);
   return LGM_OK;
 }
 

@@ -224,7 +224,7 @@ static int interp_fwd_t(void* out, const void* I, const void* u, int64_t N, int6
   dim3 grid((unsigned)cdiv(g.V, kThreads), (unsigned)N);
   const long long ibs = (NI < N) ? 0 : C * g.V;
   interp_fwd_kernel<R, D><<<grid, kThreads, 0, s>>>((R*)out, (const R*)I, (const R*)u, g, (int)C, ibs, dt);
-  count_launch();
+  count_launch("interp_fwd", s);
   return finish(s, "lgm_interp_fwd");
 }
 
@@ -247,7 +247,7 @@ static int interp_bwd_t(void* d_I, void* d_u, const void* go, const void* I, con
   else if (d_I) LAUNCH(true, false);
   else LAUNCH(false, true);
 #undef LAUNCH
-  count_launch();
+  count_launch("interp_bwd", s);
   return finish(s, "lgm_interp_bwd");
 }
 
@@ -266,7 +266,7 @@ static int regrid_t(void* dst, const void* src, int64_t N, int64_t C, const int6
   regrid_kernel<R, D, ADJ><<<grid, kThreads, 0, s>>>((R*)dst, (const R*)src, gi, go, (int)(N * C),
                                                      (R)origin[0], (R)origin[1], O2, (R)spacing[0],
                                                      (R)spacing[1], S2);
-  count_launch();
+  count_launch("regrid", s);
   return finish(s, ADJ ? "lgm_regrid_bwd" : "lgm_regrid_fwd");
 }
 

@@ -33,10 +33,18 @@ static at::Tensor wrapf(int dtype, const void* p, long N, long C, int dim, const
 static void copy_out(void* dst, const at::Tensor& t) {
   cudaMemcpy(dst, t.ptr, (size_t)t.numel() * t.itemsize(), cudaMemcpyDeviceToDevice);
 }
-#define GUARD(...)                                              \
-  try { __VA_ARGS__; cudaError_t e = cudaDeviceSynchronize();   \
-        return e == cudaSuccess ? 0 : (int)e; }                 \
-  catch (const std::exception& ex) { fprintf(stderr, "ref_cuda: %s\n", ex.what()); return -1; }
+#define GUARD(...)                                                                   \
+  try {                                                                              \
+    cudaGetLastError(); /* clear */                                                  \
+    __VA_ARGS__;                                                                     \
+    cudaError_t e = cudaGetLastError(); /* the reference never checks its launches */ \
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();                               \
+    if (e != cudaSuccess) fprintf(stderr, "ref_cuda: %s\n", cudaGetErrorString(e));  \
+    return e == cudaSuccess ? 0 : (int)e;                                            \
+  } catch (const std::exception& ex) {                                               \
+    fprintf(stderr, "ref_cuda: %s\n", ex.what());                                    \
+    return -1;                                                                       \
+  }
 
 extern "C" {
 

@@ -1,0 +1,73 @@
+"""CPU-only: host-side logic of the Python mirror (no kernels are launched)."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_identity(lm):
+    ix = lm.identity((2, 3, 4, 5, 6))
+    assert ix.shape == (2, 3, 4, 5, 6) and ix.dtype == np.float32
+    assert ix[1, 0, 3, 0, 0] == 3 and ix[0, 1, 0, 4, 0] == 4 and ix[0, 2, 0, 0, 5] == 5
+
+
+def test_regrid_argument_rules(lm):
+    from lagomorph_b200.affine import regrid_args
+    sh, o, s = regrid_args((5, 9), shape=(9, 17))
+    assert sh == (9, 17) and o == (2.0, 4.0) and s == (0.5, 0.5)
+    sh, o, s = regrid_args((5, 9, 3), shape=4)
+    assert sh == (4, 4, 4)
+    sh, o, s = regrid_args((5, 9), shape=(9, 17), spacing=2.0)
+    assert s == (2.0, 2.0) and o == (2.0, 4.0)
+    with pytest.raises(ValueError):
+        regrid_args((5, 9))
+    with pytest.raises(NotImplementedError):
+        regrid_args((5, 9), spacing=1.0)
+    with pytest.raises(ValueError):
+        regrid_args((5, 9), origin=1.0, spacing=1.0)
+    with pytest.raises(NotImplementedError):
+        regrid_args((5, 9), shape=(3, 3), origin=(0, 0))
+
+
+def test_cpu_tensors_fail_loudly(lm):
+    x = torch.zeros(1, 2, 4, 4)
+    for call in (lambda: lm.interp(x, x), lambda: lm.jacobian_times_vectorfield(x, x),
+                 lambda: lm.jacobian_times_vectorfield_adjoint(x, x), lambda: lm.FluidMetric().sharp(x),
+                 lambda: lm.Ad_star(x, x), lambda: lm.ad_star(x, x), lambda: lm.regrid(x, shape=(8, 8)),
+                 lambda: lm.expmap(lm.FluidMetric(), x)):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            call()
+
+
+def test_api_surface(lm):
+    names = ["set_debug_mode", "interp", "interp_adjoint", "jacobian_times_vectorfield",
+             "jacobian_times_vectorfield_adjoint", "FluidMetric", "Metric", "Ad_star", "ad_star", "ad", "Ad",
+             "coad", "ad_dagger", "Ad_dagger", "sym", "sym_dagger", "expmap", "expmap_advect", "EPDiff_step",
+             "EPDiffStep", "affine_interp", "affine_inverse", "regrid", "compose", "compose_disp_vel",
+             "compose_vel_disp", "identity", "LDDMMAtlasBuilder"]
+    for n in names:
+        assert hasattr(lm, n), n
+    with pytest.raises(NotImplementedError):
+        lm.Ad(None, None)
+    m = lm.FluidMetric([0.1, 0.0, 0.01])
+    assert m.params == [0.1, 0.0, 0.01]
+
+
+def test_metric_from_args(lm):
+    import argparse
+    p = argparse.ArgumentParser()
+    lm.Metric.add_args(p)
+    a = p.parse_args(["--fluid_alpha", "0.5"])
+    m = lm.Metric.from_args(a)
+    assert m.params == [0.5, 0.0, 0.01]
+
+
+def test_shard_indices():
+    from lagomorph_b200.atlas import shard_indices
+    assert shard_indices(8, 1, 0) == list(range(8))
+    assert shard_indices(8, 4, 1) == [1, 5]
+    # same as DistributedSampler(shuffle=False): pad by wrapping
+    from torch.utils.data.distributed import DistributedSampler
+    for n, w in ((10, 4), (64, 8), (7, 2)):
+        for r in range(w):
+            ds = DistributedSampler(list(range(n)), num_replicas=w, rank=r, shuffle=False)
+            assert list(ds) == shard_indices(n, w, r)
