@@ -262,15 +262,19 @@ def main():
     dom = max(ks, key=lambda k: ks[k]["ms"]) if ks else None
     roofline = None
     breakdown = {}
+    passes_per_step = {"ypass": 2}
     for k, v in ks.items():
         per_launch_ms = v["ms"] / v["launches"]
         ab = alg_bytes(k, shape)
         entry = {"launches_per_shoot": v["launches"] // main_res["kernel_reps"], "ms_per_launch": per_launch_ms,
+                 "ms_per_epdiff_step": v["ms"] / (main_res["kernel_reps"] * nsteps),
                  "share": v["ms"] / sum(x["ms"] for x in ks.values())}
         if ab is not None:
-            # every launch of these kernels covers the whole batch once
-            entry["achieved_gbs"] = ab * batch * V / (per_launch_ms * 1e-3) / 1e9
+            # algorithmic bytes of all launches of this kernel in the profiled shoots / their total time
+            total_bytes = ab * batch * V * passes_per_step.get(k, 1) * nsteps * main_res["kernel_reps"]
+            entry["achieved_gbs"] = total_bytes / (v["ms"] * 1e-3) / 1e9
             entry["frac"] = entry["achieved_gbs"] / hbm
+            entry["alg_bytes_per_launch"] = total_bytes / v["launches"]
         breakdown[k] = entry
     if dom is not None and "achieved_gbs" in breakdown[dom]:
         roofline = {"bound": "hbm", "kernel": dom, "achieved": breakdown[dom]["achieved_gbs"], "peak": hbm,

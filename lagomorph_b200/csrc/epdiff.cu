@@ -3,6 +3,7 @@
 //   m   = Ad_star(phiinv, m0)            fused gather + Jacobian        (diff.cu)
 //   v   = sharp(m)                       FFT passes + fused multiplier (fluid.cu)
 //   out = -dt*v + phiinv(x - dt*v)       fused gather + axpy           (diff.cu)
+#include <cstdlib>
 #include "common.cuh"
 
 namespace lgm {
@@ -43,20 +44,41 @@ extern "C" int lgm_epdiff_step_fwd(int dtype, void* phiinv_out, const void* phii
   for (int a = 0; a < dim; ++a) V *= shape[a];
   const size_t esz = dtype == LGM_F32 ? 4 : 8;
   const size_t field = align_up((size_t)(N * dim * V) * esz, 256);
+  // Chunked over subjects: a chunk's momentum/velocity scratch and its spectrum stay resident in L2
+  // between the five launches, so per voxel-step only phiinv, the m0 gather and the result touch HBM.
   void* m = scratch;
   void* ws = (char*)scratch + field;
-  int rc = lgm_Ad_star_fwd(dtype, m, phiinv, m0, N, dim, shape, stream);
-  if (rc) return rc;
-  if (mommask) {  // full-shape mask (N,dim,...), applied like `m = m * mommask` (lddmm.py:41-42)
-    const long long total = N * dim * V;
-    if (dtype == LGM_F32)
-      mul_mask_kernel<float><<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((float*)m, (const float*)mommask, total, total);
-    else
-      mul_mask_kernel<double><<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((double*)m, (const double*)mommask, total, total);
-    count_launch("mul_mask", (cudaStream_t)stream);
+  const size_t spec_per_subject = (size_t)dim * (V / shape[dim - 1]) * (shape[dim - 1] / 2 + 1) * 2 * esz;
+  static long long budget = -1;
+  if (budget < 0) {
+    const char* e = getenv("LGM_FLUID_CHUNK_MB");
+    budget = (e && atoll(e) > 0) ? atoll(e) << 20 : 40LL << 20;
   }
-  rc = lgm_fluid_apply(dtype, m, m, N, dim, shape, 1, alpha, beta, gamma, ws, scratch_bytes - (int64_t)field, stream);
-  if (rc) return rc;
-  // compose_disp_vel(phiinv, v, -dt) = compose(v, phiinv, ds=-dt, dt=1)  (deform.py:58-62)
-  return lgm_compose_fwd(dtype, phiinv_out, m, phiinv, N, dim, shape, -dt, 1.0, stream);
+  long long G = budget / (long long)spec_per_subject;
+  if (G < 1) G = 1;
+  if (G > N) G = N;
+  const size_t sub = (size_t)dim * V * esz;  // bytes of one subject's vector field
+  for (long long n0 = 0; n0 < N; n0 += G) {
+    const long long g = (N - n0 < G) ? (N - n0) : G;
+    const char* phi_g = (const char*)phiinv + n0 * sub;
+    const char* m0_g = (const char*)m0 + n0 * sub;
+    char* out_g = (char*)phiinv_out + n0 * sub;
+    int rc = lgm_Ad_star_fwd(dtype, m, phi_g, m0_g, g, dim, shape, stream);
+    if (rc) return rc;
+    if (mommask) {  // full-shape mask (N,dim,...), applied like `m = m * mommask` (lddmm.py:41-42)
+      const long long total = g * dim * V;
+      const char* mk = (const char*)mommask + n0 * sub;
+      if (dtype == LGM_F32)
+        mul_mask_kernel<float><<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((float*)m, (const float*)mk, total, total);
+      else
+        mul_mask_kernel<double><<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((double*)m, (const double*)mk, total, total);
+      count_launch("mul_mask", (cudaStream_t)stream);
+    }
+    rc = lgm_fluid_apply(dtype, m, m, g, dim, shape, 1, alpha, beta, gamma, ws, scratch_bytes - (int64_t)field, stream);
+    if (rc) return rc;
+    // compose_disp_vel(phiinv, v, -dt) = compose(v, phiinv, ds=-dt, dt=1)  (deform.py:58-62)
+    rc = lgm_compose_fwd(dtype, out_g, m, phi_g, g, dim, shape, -dt, 1.0, stream);
+    if (rc) return rc;
+  }
+  return LGM_OK;
 }

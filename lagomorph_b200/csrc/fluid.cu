@@ -17,6 +17,7 @@
 // direct-DFT path with the same semantics (unitary scaling in the transforms,
 // multiplier on the natural-order spectrum).
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -388,6 +389,134 @@ zinv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec, lon
   }
 }
 
+// Slab forward (3-D): one CTA owns one x-slab of one channel: Y real lines of Z points are
+// staged in shared memory as tile[rz*P + y] (P = Y+1, odd), transformed along z (half-length
+// complex FFT + split, lanes over y) and then along y (lanes over rz, stride P => conflict
+// free), and leave as the spectrum slab [ry][rz]. Replaces zfwd + ypass (one global round trip
+// of the spectrum less) whenever (Z/2+1)*(Y+1) complex words fit in shared memory.
+template <typename R, int Y, int Z>
+__global__ void __launch_bounds__(kFftThreads)
+slab_fwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in,
+                const typename Cx<R>::T* __restrict__ twz_g, const typename Cx<R>::T* __restrict__ twy_g) {
+  using C = typename Cx<R>::T;
+  constexpr int M = Z / 2, P = Y + 1, ZC = M + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* tile = reinterpret_cast<C*>(smem_raw);  // ZC x P
+  C* twz = tile + ZC * P;                    // Z entries
+  C* twM = twz + Z;                          // M entries (W_M^j = W_Z^2j)
+  C* twy = twM + M;                          // Y entries
+  const int tid = threadIdx.x;
+  for (int j = tid; j < Z; j += kFftThreads) twz[j] = twz_g[j];
+  for (int j = tid; j < M; j += kFftThreads) twM[j] = twz_g[2 * j];
+  for (int j = tid; j < Y; j += kFftThreads) twy[j] = twy_g[j];
+  const C* in2 = reinterpret_cast<const C*>(in) + (size_t)blockIdx.x * Y * M;
+#pragma unroll 4
+  for (int idx = tid; idx < Y * M; idx += kFftThreads) {
+    const int y = idx / M, j = idx % M;
+    tile[j * P + y] = in2[idx];
+  }
+  __syncthreads();
+  col_fft_fwd<R, M, Y>(tile, P, 1, twM, tid, kFftThreads);
+  __syncthreads();
+  for (int idx = tid; idx < Y * (M / 2 + 1); idx += kFftThreads) {
+    const int l = idx % Y, k = idx / Y;
+    if (k == 0) {
+      C a = tile[l];
+      C x0, xm;
+      x0.x = a.x + a.y; x0.y = R(0);
+      xm.x = a.x - a.y; xm.y = R(0);
+      tile[l] = x0;
+      tile[M * P + l] = xm;
+    } else {
+      const int pa = fft_pos<M>(k), pb = fft_pos<M>(M - k);
+      C a = tile[pa * P + l], b = tile[pb * P + l], w = twz[k];
+      C s, d, t, xk, xm, w2, d2, t2;
+      s.x = a.x + b.x; s.y = a.y - b.y;
+      d.x = a.x - b.x; d.y = a.y + b.y;
+      t = cmul(w, d);
+      xk.x = R(0.5) * (s.x + t.y);
+      xk.y = R(0.5) * (s.y - t.x);
+      w2.x = -w.x; w2.y = w.y;
+      d2.x = -d.x; d2.y = d.y;
+      t2 = cmul(w2, d2);
+      xm.x = R(0.5) * (s.x + t2.y);
+      xm.y = R(0.5) * (-s.y - t2.x);
+      tile[pa * P + l] = xk;
+      if (pb != pa) tile[pb * P + l] = xm;
+    }
+  }
+  __syncthreads();
+  col_fft_fwd<R, Y, ZC>(tile, 1, P, twy, tid, kFftThreads);
+  __syncthreads();
+  C* o = spec + (size_t)blockIdx.x * Y * ZC;
+#pragma unroll 4
+  for (int idx = tid; idx < Y * ZC; idx += kFftThreads) {
+    const int ry = idx / ZC, rz = idx % ZC;
+    o[idx] = tile[rz * P + ry];
+  }
+}
+
+// Slab inverse: mirror of slab_fwd_kernel (spectrum slab -> Y real lines), unnormalised.
+template <typename R, int Y, int Z>
+__global__ void __launch_bounds__(kFftThreads)
+slab_inv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec,
+                const typename Cx<R>::T* __restrict__ twz_g, const typename Cx<R>::T* __restrict__ twy_g) {
+  using C = typename Cx<R>::T;
+  constexpr int M = Z / 2, P = Y + 1, ZC = M + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* tile = reinterpret_cast<C*>(smem_raw);
+  C* twz = tile + ZC * P;
+  C* twM = twz + Z;
+  C* twy = twM + M;
+  const int tid = threadIdx.x;
+  for (int j = tid; j < Z; j += kFftThreads) twz[j] = twz_g[j];
+  for (int j = tid; j < M; j += kFftThreads) twM[j] = twz_g[2 * j];
+  for (int j = tid; j < Y; j += kFftThreads) twy[j] = twy_g[j];
+  const C* sp = spec + (size_t)blockIdx.x * Y * ZC;
+#pragma unroll 4
+  for (int idx = tid; idx < Y * ZC; idx += kFftThreads) {
+    const int ry = idx / ZC, rz = idx % ZC;
+    tile[rz * P + ry] = sp[idx];
+  }
+  __syncthreads();
+  col_fft_inv<R, Y, ZC>(tile, 1, P, twy, tid, kFftThreads);
+  __syncthreads();
+  for (int idx = tid; idx < Y * (M / 2 + 1); idx += kFftThreads) {
+    const int l = idx % Y, k = idx / Y;
+    if (k == 0) {
+      R r0 = tile[l].x, rm = tile[M * P + l].x;
+      C z;
+      z.x = r0 + rm;
+      z.y = r0 - rm;
+      tile[l] = z;
+    } else {
+      const int pa = fft_pos<M>(k), pb = fft_pos<M>(M - k);
+      C a = tile[pa * P + l], b = tile[pb * P + l], w = twz[k];
+      C s, d, t, zk, zm, d2, t2;
+      s.x = a.x + b.x; s.y = a.y - b.y;
+      d.x = a.x - b.x; d.y = a.y + b.y;
+      t = cmulc(d, w);
+      zk.x = s.x - t.y;
+      zk.y = s.y + t.x;
+      d2.x = -d.x; d2.y = d.y;
+      t2 = cmul(d2, w);
+      zm.x = s.x + t2.y;
+      zm.y = -s.y - t2.x;
+      tile[pa * P + l] = zk;
+      if (pb != pa) tile[pb * P + l] = zm;
+    }
+  }
+  __syncthreads();
+  col_fft_inv<R, M, Y>(tile, P, 1, twM, tid, kFftThreads);
+  __syncthreads();
+  C* o2 = reinterpret_cast<C*>(out) + (size_t)blockIdx.x * Y * M;
+#pragma unroll 4
+  for (int idx = tid; idx < Y * M; idx += kFftThreads) {
+    const int y = idx / M, j = idx % M;
+    o2[idx] = tile[j * P + y];
+  }
+}
+
 // Y pass (3-D only): in-place column FFT over the middle axis on [NY x T] tiles.
 // grid = (ceil(Zc/T), X, N*dim)
 template <typename R, int NY, int T, bool INV>
@@ -677,6 +806,48 @@ struct FastLaunch {
     default: break;                                        \
   }
 
+// Slab path launchers (3-D, Y == Z in {16,32,64,128}); LGM_EUNSUP when the shape has no slab kernel.
+template <typename R, int YZ>
+static int slab_launch(bool inv, void* real, typename Cx<R>::T* spec, long long slabs, const FluidPlan& p,
+                       cudaStream_t s) {
+  using C = typename Cx<R>::T;
+  constexpr int M = YZ / 2;
+  const size_t smem = sizeof(C) * ((size_t)(M + 1) * (YZ + 1) + YZ + M + YZ);
+  if (!inv) {
+    LGM_CUDA_TRY(set_smem(slab_fwd_kernel<R, YZ, YZ>, smem), "slab_fwd smem");
+    slab_fwd_kernel<R, YZ, YZ><<<(unsigned)slabs, kFftThreads, smem, s>>>(spec, (const R*)real, (const C*)p.tw[2], (const C*)p.tw[1]);
+    count_launch("slab_fwd", s);
+  } else {
+    LGM_CUDA_TRY(set_smem(slab_inv_kernel<R, YZ, YZ>, smem), "slab_inv smem");
+    slab_inv_kernel<R, YZ, YZ><<<(unsigned)slabs, kFftThreads, smem, s>>>((R*)real, spec, (const C*)p.tw[2], (const C*)p.tw[1]);
+    count_launch("slab_inv", s);
+  }
+  return LGM_OK;
+}
+template <typename R>
+static int slab_pass(bool inv, int Y, int Z, void* real, typename Cx<R>::T* spec, long long slabs,
+                     const FluidPlan& p, cudaStream_t s) {
+  if (Y != Z) return LGM_EUNSUP;
+  switch (Y) {
+    case 16: return slab_launch<R, 16>(inv, real, spec, slabs, p, s);
+    case 32: return slab_launch<R, 32>(inv, real, spec, slabs, p, s);
+    case 64: return slab_launch<R, 64>(inv, real, spec, slabs, p, s);
+    case 128: return slab_launch<R, 128>(inv, real, spec, slabs, p, s);
+    default: return LGM_EUNSUP;
+  }
+}
+
+// Subjects are pushed through all passes in chunks small enough for the chunk's spectrum to stay
+// resident in the 126 MB L2, so that only the first read and the last write of a chunk go to HBM.
+static long long chunk_budget_bytes() {
+  static long long v = -1;
+  if (v < 0) {
+    const char* e = getenv("LGM_FLUID_CHUNK_MB");
+    v = (e && atoll(e) > 0) ? atoll(e) << 20 : 40LL << 20;
+  }
+  return v;
+}
+
 template <typename R>
 static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64_t* shape,
                       int inverse, double alpha, double beta, double gamma, void* ws,
@@ -684,36 +855,59 @@ static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64
   using C = typename Cx<R>::T;
   using FL = FastLaunch<R>;
   constexpr int MAXN = sizeof(R) == 4 ? 512 : 256;
-  const int X = (int)shape[0], Y = (int)shape[1], Z = dim == 3 ? (int)shape[2] : 0;
+  const int X = (int)shape[0], Y = (int)shape[1];
   const int nlast = (int)shape[dim - 1];
   const int Zc = nlast / 2 + 1;
   long long V = 1;
   for (int a = 0; a < dim; ++a) V *= shape[a];
-  const long long rows = N * dim * (V / nlast);
   C* spec = (C*)ws;
   const R scale = (R)(1.0 / (double)V);
-  int rc = LGM_EUNSUP;
-  LGM_SWITCH_Z(nlast, MAXN, rc = FL::template zfwd<NN>(spec, (const R*)in, rows, (const C*)p.tw[dim - 1], s));
-  if (rc) return rc == LGM_EUNSUP ? set_error(rc, "lgm_fluid_apply: unsupported size") : rc;
-  if (dim == 3) {
-    rc = LGM_EUNSUP;
-    LGM_SWITCH_POW2(Y, MAXN, rc = (FL::template ypass<NN, false>(spec, (int)(N * dim), X, Zc, (const C*)p.tw[1], s)));
-    if (rc) return rc;
-    rc = LGM_EUNSUP;
-    LGM_SWITCH_POW2(X, MAXN, rc = (FL::template xpass<NN, 3>(spec, N, (long long)Y * Zc, Zc, p, inverse, alpha, beta, gamma, scale, s)));
-    if (rc) return rc;
-    rc = LGM_EUNSUP;
-    LGM_SWITCH_POW2(Y, MAXN, rc = (FL::template ypass<NN, true>(spec, (int)(N * dim), X, Zc, (const C*)p.tw[1], s)));
-    if (rc) return rc;
-  } else {
-    rc = LGM_EUNSUP;
-    LGM_SWITCH_POW2(X, MAXN, rc = (FL::template xpass<NN, 2>(spec, N, (long long)Zc, Zc, p, inverse, alpha, beta, gamma, scale, s)));
+  const long long spec_bytes_per_subject = (long long)dim * (V / nlast) * Zc * sizeof(C);
+  long long G = chunk_budget_bytes() / spec_bytes_per_subject;
+  if (G < 1) G = 1;
+  if (G > N) G = N;
+  for (long long n0 = 0; n0 < N; n0 += G) {
+    const long long g = (N - n0 < G) ? (N - n0) : G;
+    const R* in_g = (const R*)in + n0 * dim * V;
+    R* out_g = (R*)out + n0 * dim * V;
+    const long long rows = g * dim * (V / nlast);
+    int rc = LGM_EUNSUP;
+    if (dim == 3) rc = slab_pass<R>(false, Y, nlast, (void*)in_g, spec, g * dim * X, p, s);
+    const bool slab = (rc == LGM_OK);
+    if (rc != LGM_OK && rc != LGM_EUNSUP) return rc;
+    if (!slab) {
+      rc = LGM_EUNSUP;
+      LGM_SWITCH_Z(nlast, MAXN, rc = FL::template zfwd<NN>(spec, in_g, rows, (const C*)p.tw[dim - 1], s));
+      if (rc) return rc == LGM_EUNSUP ? set_error(rc, "lgm_fluid_apply: unsupported size") : rc;
+    }
+    if (dim == 3) {
+      if (!slab) {
+        rc = LGM_EUNSUP;
+        LGM_SWITCH_POW2(Y, MAXN, rc = (FL::template ypass<NN, false>(spec, (int)(g * dim), X, Zc, (const C*)p.tw[1], s)));
+        if (rc) return rc;
+      }
+      rc = LGM_EUNSUP;
+      LGM_SWITCH_POW2(X, MAXN, rc = (FL::template xpass<NN, 3>(spec, g, (long long)Y * Zc, Zc, p, inverse, alpha, beta, gamma, scale, s)));
+      if (rc) return rc;
+      if (!slab) {
+        rc = LGM_EUNSUP;
+        LGM_SWITCH_POW2(Y, MAXN, rc = (FL::template ypass<NN, true>(spec, (int)(g * dim), X, Zc, (const C*)p.tw[1], s)));
+        if (rc) return rc;
+      }
+    } else {
+      rc = LGM_EUNSUP;
+      LGM_SWITCH_POW2(X, MAXN, rc = (FL::template xpass<NN, 2>(spec, g, (long long)Zc, Zc, p, inverse, alpha, beta, gamma, scale, s)));
+      if (rc) return rc;
+    }
+    if (slab) {
+      rc = slab_pass<R>(true, Y, nlast, (void*)out_g, spec, g * dim * X, p, s);
+    } else {
+      rc = LGM_EUNSUP;
+      LGM_SWITCH_Z(nlast, MAXN, rc = FL::template zinv<NN>(out_g, spec, rows, (const C*)p.tw[dim - 1], s));
+    }
     if (rc) return rc;
   }
-  (void)Z;
-  rc = LGM_EUNSUP;
-  LGM_SWITCH_Z(nlast, MAXN, rc = FL::template zinv<NN>((R*)out, spec, rows, (const C*)p.tw[dim - 1], s));
-  return rc;
+  return LGM_OK;
 }
 
 template <typename R, int D>
