@@ -52,7 +52,7 @@ extern "C" int lgm_epdiff_step_fwd(int dtype, void* phiinv_out, const void* phii
   static long long budget = -1;
   if (budget < 0) {
     const char* e = getenv("LGM_FLUID_CHUNK_MB");
-    budget = (e && atoll(e) > 0) ? atoll(e) << 20 : 40LL << 20;
+    budget = (e && atoll(e) > 0) ? atoll(e) << 20 : 1LL << 50;  // default: no chunking (see fluid.cu)
   }
   long long G = budget / (long long)spec_per_subject;
   if (G < 1) G = 1;

@@ -162,6 +162,70 @@ __device__ __forceinline__ void fft_stage(typename Cx<R>::T* tile, int rs, int l
   }
 }
 
+// Outermost stage (BLOCK == N) with one side in GLOBAL memory: the forward transform's first
+// stage reads its RAD inputs straight from global memory (row stride grs, lanes along l are
+// consecutive words => coalesced) and stores to the shared tile; the inverse transform's last
+// stage reads the tile and stores straight to global. Columns l >= lvalid are padding.
+template <typename R, int N, int RAD, int L, bool INV>
+__device__ __forceinline__ void fft_stage_edge(typename Cx<R>::T* __restrict__ g, long long grs,
+                                               typename Cx<R>::T* tile, int rs, int ls,
+                                               const typename Cx<R>::T* __restrict__ tw, int lvalid,
+                                               int tid, int nth) {
+  using C = typename Cx<R>::T;
+  constexpr int SUB = N / RAD;
+  constexpr int ITEMS = L * SUB;
+  constexpr int BITS = ilog2(RAD);
+  for (int it = tid; it < ITEMS; it += nth) {
+    const int l = it % L, rest = it / L;
+    C* p = tile + rest * rs + l * ls;
+    C* gp = g + (long long)rest * grs + l;
+    const bool ok = l < lvalid;
+    C x[RAD];
+    if (!INV) {
+#pragma unroll
+      for (int n = 0; n < RAD; ++n) {
+        C v;
+        v.x = v.y = R(0);
+        if (ok) v = gp[(long long)n * SUB * grs];
+        x[n] = v;
+      }
+      reg_fft<RAD, false>(x);
+#pragma unroll
+      for (int i = 0; i < RAD; ++i) {
+        const int k = bitrev(i, BITS);
+        C v = x[i];
+        if (SUB > 1 && k != 0) v = cmul(v, tw[rest * k]);
+        p[k * SUB * rs] = v;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < RAD; ++k) {
+        C v = p[k * SUB * rs];
+        if (SUB > 1 && k != 0) v = cmulc(v, tw[rest * k]);
+        x[k] = v;
+      }
+      reg_fft<RAD, true>(x);
+      if (ok) {
+#pragma unroll
+        for (int i = 0; i < RAD; ++i) gp[(long long)bitrev(i, BITS) * SUB * grs] = x[i];
+      }
+    }
+  }
+}
+
+// forward: global -> (first stage) -> tile -> remaining stages in the tile
+template <typename R, int N, int L>
+__device__ __forceinline__ void col_fft_fwd_from_global(typename Cx<R>::T* g, long long grs,
+                                                        typename Cx<R>::T* tile, int rs, int ls,
+                                                        const typename Cx<R>::T* tw, int lvalid,
+                                                        int tid, int nth);
+// inverse: tile -> inner stages -> (last stage) -> global
+template <typename R, int N, int L>
+__device__ __forceinline__ void col_fft_inv_to_global(typename Cx<R>::T* g, long long grs,
+                                                      typename Cx<R>::T* tile, int rs, int ls,
+                                                      const typename Cx<R>::T* tw, int lvalid,
+                                                      int tid, int nth);
+
 template <typename R, int N, int BLOCK, int SI, int L>
 struct ColFFT {
   using C = typename Cx<R>::T;
@@ -193,6 +257,36 @@ template <typename R, int N, int L>
 __device__ __forceinline__ void col_fft_inv(typename Cx<R>::T* tile, int rs, int ls,
                                             const typename Cx<R>::T* tw, int tid, int nth) {
   if constexpr (N > 1) ColFFT<R, N, N, 0, L>::inv(tile, rs, ls, tw, tid, nth);
+}
+
+}  // namespace lgm
+
+namespace lgm {
+
+template <typename R, int N, int L>
+__device__ __forceinline__ void col_fft_fwd_from_global(typename Cx<R>::T* g, long long grs,
+                                                        typename Cx<R>::T* tile, int rs, int ls,
+                                                        const typename Cx<R>::T* tw, int lvalid,
+                                                        int tid, int nth) {
+  constexpr int RAD = 1 << stage_bits(ilog2(N), 0);
+  fft_stage_edge<R, N, RAD, L, false>(g, grs, tile, rs, ls, tw, lvalid, tid, nth);
+  if constexpr (N / RAD > 1) {
+    __syncthreads();
+    ColFFT<R, N, N / RAD, 1, L>::fwd(tile, rs, ls, tw, tid, nth);
+  }
+}
+
+template <typename R, int N, int L>
+__device__ __forceinline__ void col_fft_inv_to_global(typename Cx<R>::T* g, long long grs,
+                                                      typename Cx<R>::T* tile, int rs, int ls,
+                                                      const typename Cx<R>::T* tw, int lvalid,
+                                                      int tid, int nth) {
+  constexpr int RAD = 1 << stage_bits(ilog2(N), 0);
+  if constexpr (N / RAD > 1) {
+    ColFFT<R, N, N / RAD, 1, L>::inv(tile, rs, ls, tw, tid, nth);
+    __syncthreads();
+  }
+  fft_stage_edge<R, N, RAD, L, true>(g, grs, tile, rs, ls, tw, lvalid, tid, nth);
 }
 
 }  // namespace lgm

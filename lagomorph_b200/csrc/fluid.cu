@@ -637,6 +637,113 @@ xpass_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
 }
 
 // ------------------------------------------------------------------------------------------
+// X pass, second generation. Same tiling as xpass_kernel, but
+//  - the first forward stage loads its radix inputs straight from global memory and the last
+//    inverse stage stores straight to global memory (no staging copy of the tile, two fewer
+//    shared-memory round trips per element);
+//  - a thread keeps one column l = tid % T for the whole kernel, so the (y,z) part of the symbol
+//    (LUT lookups, the q -> (ry, rz) division) is computed once per thread, not once per element;
+//  - beta == 0 path: reciprocal square root in fp32 round-to-nearest intrinsics (equal to the
+//    reference's double division rounded to float except on double-rounding ties).
+template <typename R>
+__device__ __forceinline__ R oo_sqrt_fast(R x) {
+  if constexpr (sizeof(R) == 4) {
+    float s = ((double)x < 1e-8) ? 1e-4f : __fsqrt_rn((float)x);
+    return (R)__frcp_rn(s);
+  } else {
+    return oo_sqrt<R>(x);
+  }
+}
+
+template <typename R, int NX, int T, int D, int NCH, bool INVERSE>
+__global__ void __launch_bounds__(kFftThreads)
+xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
+              const typename Cx<R>::T* __restrict__ tw_g, const R* __restrict__ wl0,
+              const R* __restrict__ sl0, const R* __restrict__ wl1, const R* __restrict__ sl1,
+              const R* __restrict__ wl2, const R* __restrict__ sl2, double alpha, double beta,
+              double gamma, R scale) {
+  using C = typename Cx<R>::T;
+  static_assert(kFftThreads % T == 0, "a thread must own one column");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* tile = reinterpret_cast<C*>(smem_raw);  // NCH x NX x T
+  C* tw = tile + NCH * NX * T;
+  R* lx = reinterpret_cast<R*>(tw + NX);     // wl0[NX] (+ sl0[NX] when NCH > 1)
+  const int tid = threadIdx.x;
+  for (int j = tid; j < NX; j += kFftThreads) {
+    tw[j] = tw_g[j];
+    lx[j] = wl0[j];
+    if (NCH > 1) lx[NX + j] = sl0[j];
+  }
+  const long long q0 = (long long)blockIdx.x * T;
+  const int lvalid = (int)((plane - q0 < T) ? (plane - q0) : T);
+  C* base = spec + (long long)blockIdx.y * NCH * NX * plane + q0;
+  // per-thread (y,z) part of the symbol
+  const int l = tid % T;
+  R wy = R(0), wz = R(0), sy = R(0), sz = R(0);
+  if (l < lvalid) {
+    const long long q = q0 + l;
+    if constexpr (D == 2) {
+      wy = wl1[q];
+      if (NCH > 1) sy = sl1[q];
+    } else {
+      const int py = (int)(q / Zc), pz = (int)(q - (long long)py * Zc);
+      wy = wl1[py];
+      wz = wl2[pz];
+      if (NCH > 1) { sy = sl1[py]; sz = sl2[pz]; }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch)
+    col_fft_fwd_from_global<R, NX, T>(base + (long long)ch * NX * plane, plane, tile + ch * NX * T, T, 1, tw,
+                                      lvalid, tid, kFftThreads);
+  __syncthreads();
+  for (int idx = tid; idx < NX * T; idx += kFftThreads) {  // idx % T == l for every iteration
+    const int r = idx / T;
+    R w[3] = {lx[r], wy, wz};
+    if constexpr (NCH == 1) {
+      R sw = (D == 2) ? (w[0] + w[1]) : (w[0] + w[1] + w[2]);
+      const R lambda = (R)(gamma + alpha * (double)sw);
+      const R Lm = lambda * lambda;
+      C v = tile[idx];
+      if (INVERSE) {
+        const R f = oo_sqrt_fast<R>(Lm);
+        v.x = ((v.x * f) * f) * scale;
+        v.y = ((v.y * f) * f) * scale;
+      } else {
+        v.x = (Lm * v.x) * scale;
+        v.y = (Lm * v.y) * scale;
+      }
+      tile[idx] = v;
+    } else {
+      R s[3] = {lx[NX + r], sy, sz};
+      Symbol<R, D> S = make_symbol<R, D, INVERSE>(w, s, alpha, beta, gamma);
+      R re[D], im[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        C v = tile[c * NX * T + idx];
+        re[c] = v.x;
+        im[c] = v.y;
+      }
+      apply_symbol<R, D, INVERSE>(S, re);
+      apply_symbol<R, D, INVERSE>(S, im);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        C v;
+        v.x = re[c] * scale;
+        v.y = im[c] * scale;
+        tile[c * NX * T + idx] = v;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch)
+    col_fft_inv_to_global<R, NX, T>(base + (long long)ch * NX * plane, plane, tile + ch * NX * T, T, 1, tw,
+                                    lvalid, tid, kFftThreads);
+}
+
+// ------------------------------------------------------------------------------------------
 // Direct-DFT path (any size): unitary transforms, out of place between two buffers.
 // ------------------------------------------------------------------------------------------
 // real lines (rows x n) -> (rows x nc) complex, scaled
@@ -761,10 +868,12 @@ struct FastLaunch {
   template <int NX, int D, int NCH, bool INVERSE>
   static int xpass1(C* spec, long long N, long long plane, int Zc, const FluidPlan& p, double alpha,
                     double beta, double gamma, R scale, cudaStream_t s) {
-    const size_t smem = sizeof(C) * ((size_t)NCH * NX * T + NX);
-    LGM_CUDA_TRY(set_smem(xpass_kernel<R, NX, T, D, NCH, INVERSE>, smem), "xpass smem");
-    dim3 grid((unsigned)cdiv(plane, T), (unsigned)(NCH == 1 ? N * D : N));
-    xpass_kernel<R, NX, T, D, NCH, INVERSE><<<grid, kFftThreads, smem, s>>>(
+    // tile width: 32 words (256 B runs) while the tile stays small, else the class default
+    constexpr int TX = (sizeof(R) == 4 && NCH * NX <= 128) ? 32 : T;
+    const size_t smem = sizeof(C) * ((size_t)NCH * NX * TX + NX) + sizeof(R) * 2 * NX;
+    LGM_CUDA_TRY(set_smem(xpass2_kernel<R, NX, TX, D, NCH, INVERSE>, smem), "xpass smem");
+    dim3 grid((unsigned)cdiv(plane, TX), (unsigned)(NCH == 1 ? N * D : N));
+    xpass2_kernel<R, NX, TX, D, NCH, INVERSE><<<grid, kFftThreads, smem, s>>>(
         spec, plane, Zc, (const C*)p.tw[0], (const R*)p.wl[0], (const R*)p.sl[0], (const R*)p.wl[1],
         (const R*)p.sl[1], (const R*)p.wl[2], (const R*)p.sl[2], alpha, beta, gamma, scale);
     count_launch("xpass", s);
@@ -843,7 +952,9 @@ static long long chunk_budget_bytes() {
   static long long v = -1;
   if (v < 0) {
     const char* e = getenv("LGM_FLUID_CHUNK_MB");
-    v = (e && atoll(e) > 0) ? atoll(e) << 20 : 40LL << 20;
+    // default: no chunking. Measured on B200 (profiles/r1_notes.md): while the passes are bound by
+    // SM work rather than HBM, smaller launches only add tail and launch-gap time.
+    v = (e && atoll(e) > 0) ? atoll(e) << 20 : 1LL << 50;
   }
   return v;
 }

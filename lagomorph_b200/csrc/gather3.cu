@@ -34,129 +34,132 @@ struct Ax3 {
   float t;
 };
 
+// floor / fraction / clamped corner indices of one coordinate. Coordinates are first clamped to
+// +-2^22 voxels (far outside any volume: both corners are the border voxel there, and the result is
+// the border value for any weight), which lets floor() be a magic-number add with no slow path.
 __device__ __forceinline__ Ax3 axis_fast(float x, int n) {
   Ax3 a;
-  int f;
-  if (fabsf(x) < 4194304.f) {
-    float r = __fadd_rn(x, 12582912.f);  // 1.5 * 2^23: rounds x to an integer in the mantissa
-    f = __float_as_int(r) - 0x4B400000;
-    float rf = __fsub_rn(r, 12582912.f);
-    if (rf > x) {
-      rf -= 1.f;
-      f -= 1;
-    }
-    a.t = x - rf;
-  } else {
-    a.t = x - floorf(x);
-    f = __float2int_rd(x);
-    if (f == 0x7fffffff) f = 0x7ffffffe;
+  x = fminf(fmaxf(x, -4194304.f), 4194304.f);
+  float r = __fadd_rn(x, 12582912.f);  // 1.5 * 2^23: rounds x to an integer in the mantissa
+  int f = __float_as_int(r) - 0x4B400000;
+  float rf = __fsub_rn(r, 12582912.f);
+  if (rf > x) {
+    rf -= 1.f;
+    f -= 1;
   }
+  a.t = x - rf;
   a.i0 = min(max(f, 0), n - 1);
   a.i1 = min(max(f + 1, 0), n - 1);
   return a;
 }
 
-__device__ __forceinline__ float trilerp(const float* __restrict__ img, int o00, int o01, int o10,
-                                         int o11, const Ax3& az, float t, float u, float v) {
-  // corner numbering / evaluation order of include/interp.h:91-122
-  float v0 = __ldg(img + o00 + az.i0), v4 = __ldg(img + o00 + az.i1);
-  float v3 = __ldg(img + o01 + az.i0), v7 = __ldg(img + o01 + az.i1);
-  float v1 = __ldg(img + o10 + az.i0), v5 = __ldg(img + o10 + az.i1);
-  float v2 = __ldg(img + o11 + az.i0), v6 = __ldg(img + o11 + az.i1);
-  float omt = 1.f - t, omu = 1.f - u, omv = 1.f - v;
+// 8-corner gather + nested lerp (corner numbering / evaluation order of include/interp.h:91-122).
+// i00..i11 are the element indices of the four (x,y) corner rows at the lower z corner; the upper z
+// corner is always the +1 neighbour (an immediate offset on the same address register), see z_pair().
+__device__ __forceinline__ float trilerp(const float* __restrict__ img, unsigned i00, unsigned i01,
+                                         unsigned i10, unsigned i11, float t, float u, float v,
+                                         float omt, float omu, float omv) {
+  const float* p00 = img + i00;
+  const float* p01 = img + i01;
+  const float* p10 = img + i10;
+  const float* p11 = img + i11;
+  float v0 = __ldg(p00), v4 = __ldg(p00 + 1);
+  float v3 = __ldg(p01), v7 = __ldg(p01 + 1);
+  float v1 = __ldg(p10), v5 = __ldg(p10 + 1);
+  float v2 = __ldg(p11), v6 = __ldg(p11 + 1);
   return omv * (omu * (omt * v0 + t * v1) + u * (omt * v3 + t * v2)) +
          v * (omu * (omt * v4 + t * v5) + u * (omt * v7 + t * v6));
 }
 
-__device__ __forceinline__ float f4get(const float4& v, int i) {
-  return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+// Along the contiguous axis the two corners are fetched as (zs, zs+1) with zs <= Z-2 so that the
+// pair never leaves the row. Where the reference clamps both corners onto one border voxel
+// ((1-v)*B + v*B) the weight is replaced by 0 (lower border) or 1 (upper border): the same value
+// up to the rounding of (1-v)*B + v*B, i.e. <= 1 ulp, and only outside the volume.
+__device__ __forceinline__ void z_pair(const Ax3& az, int Z, int& zs, float& v) {
+  zs = min(az.i0, Z - 2);
+  v = az.t;
+  if (az.i1 == az.i0) v = (az.i0 == 0) ? 0.f : 1.f;
 }
 
-// MODE 0: Ad_star (a = phiinv, b = m0); MODE 1: compose (a = u, b = v)
-template <int MODE>
+// MODE 0: Ad_star (a = phiinv, b = m0); MODE 1: compose (a = u, b = v).
+// blockDim = (32, 8): a warp walks one z row (lane = z, NV chunks of 32), a CTA covers 8 y rows.
+template <int MODE, int NV>
 __global__ void __launch_bounds__(256)
 gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
                int X, int Y, int Z, float dh, float dl, float dsr, float dtr) {
-  const int k0 = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int j = blockIdx.y * 8 + threadIdx.y;
-  if (k0 >= Z || j >= Y) return;
+  if (j >= Y) return;
   const int i = blockIdx.z % X;
   const int n = blockIdx.z / X;
   const int sy = Z, sx = Y * Z;
-  const size_t V = (size_t)X * sx;
+  const int V = X * sx;
   const float* an = a + (size_t)n * 3 * V;
   const float* bn = b + (size_t)n * 3 * V;
+  const float* bn1 = bn + V;
+  const float* bn2 = bn1 + V;
   float* on = out + (size_t)n * 3 * V;
-  const int c0 = i * sx + j * sy + k0;
-
-  float4 A[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) A[c] = __ldg(reinterpret_cast<const float4*>(an + c * V + c0));
-
-  float val[3][4];
+  // keep the per-subject channel bases as plain 64-bit registers so that every gather address is
+  // one IMAD.WIDE.U32 (base + 4*index) instead of a 64-bit add chain
+  asm volatile("" : "+l"(bn), "+l"(bn1), "+l"(bn2));
+  const int row = i * sx + j * sy;
   const float fi = (float)i, fj = (float)j;
+  const int xm = (i > 0) ? -sx : 0, xp = (i < X - 1) ? sx : 0;
+  const int ym = (j > 0) ? -sy : 0, yp = (j < Y - 1) ? sy : 0;
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
+  for (int v = 0; v < NV; ++v) {
+    const int k = (blockIdx.x * NV + v) * 32 + threadIdx.x;
+    if (k >= Z) break;
+    const int c0 = row + k;
+    const float* a0 = an + c0;
+    const float* a1 = a0 + V;
+    const float* a2 = a1 + V;
+    const float A0 = __ldg(a0), A1 = __ldg(a1), A2 = __ldg(a2);
     float hx, hy, hz;
-    const float fk = (float)(k0 + v);
+    const float fk = (float)k;
     if (MODE == 0) {  // dt == 1: the double sum is exact before rounding
-      hx = __fadd_rn(fi, f4get(A[0], v));
-      hy = __fadd_rn(fj, f4get(A[1], v));
-      hz = __fadd_rn(fk, f4get(A[2], v));
+      hx = __fadd_rn(fi, A0);
+      hy = __fadd_rn(fj, A1);
+      hz = __fadd_rn(fk, A2);
     } else {
-      hx = coord_f32(fi, f4get(A[0], v), dh, dl);
-      hy = coord_f32(fj, f4get(A[1], v), dh, dl);
-      hz = coord_f32(fk, f4get(A[2], v), dh, dl);
+      hx = coord_f32(fi, A0, dh, dl);
+      hy = coord_f32(fj, A1, dh, dl);
+      hz = coord_f32(fk, A2, dh, dl);
     }
     const Ax3 ax = axis_fast(hx, X), ay = axis_fast(hy, Y), az = axis_fast(hz, Z);
-    const int o00 = ax.i0 * sx + ay.i0 * sy, o01 = ax.i0 * sx + ay.i1 * sy;
-    const int o10 = ax.i1 * sx + ay.i0 * sy, o11 = ax.i1 * sx + ay.i1 * sy;
+    int zs;
+    float wv;
+    z_pair(az, Z, zs, wv);
+    const unsigned rx0 = ax.i0 * sx + zs, rx1 = ax.i1 * sx + zs;
+    const unsigned ry0 = ay.i0 * sy, ry1 = ay.i1 * sy;
+    const unsigned i00 = rx0 + ry0, i01 = rx0 + ry1, i10 = rx1 + ry0, i11 = rx1 + ry1;
+    const float omt = 1.f - ax.t, omu = 1.f - ay.t, omv = 1.f - wv;
+    const float m0v = trilerp(bn, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv);
+    const float m1v = trilerp(bn1, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv);
+    const float m2v = trilerp(bn2, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv);
+    if (MODE == 1) {
+      on[c0] = __fadd_rn(__fmul_rn(dsr, A0), __fmul_rn(dtr, m0v));
+      on[c0 + V] = __fadd_rn(__fmul_rn(dsr, A1), __fmul_rn(dtr, m1v));
+      on[c0 + 2 * V] = __fadd_rn(__fmul_rn(dsr, A2), __fmul_rn(dtr, m2v));
+    } else {
+      const int zm = (k > 0) ? -1 : 0, zp = (k < Z - 1) ? 1 : 0;
+      const float* ac[3] = {a0, a1, a2};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) val[c][v] = trilerp(bn + c * V, o00, o01, o10, o11, az, ax.t, ay.t, az.t);
-  }
-
-  if (MODE == 1) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float4 o;
-      o.x = __fadd_rn(__fmul_rn(dsr, A[c].x), __fmul_rn(dtr, val[c][0]));
-      o.y = __fadd_rn(__fmul_rn(dsr, A[c].y), __fmul_rn(dtr, val[c][1]));
-      o.z = __fadd_rn(__fmul_rn(dsr, A[c].z), __fmul_rn(dtr, val[c][2]));
-      o.w = __fadd_rn(__fmul_rn(dsr, A[c].w), __fmul_rn(dtr, val[c][3]));
-      *reinterpret_cast<float4*>(on + c * V + c0) = o;
-    }
-  } else {
-    const int xm = (i > 0) ? -sx : 0, xp = (i < X - 1) ? sx : 0;
-    const int ym = (j > 0) ? -sy : 0, yp = (j < Y - 1) ? sy : 0;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* ac = an + c * V + c0;
-      const float4 XM = __ldg(reinterpret_cast<const float4*>(ac + xm));
-      const float4 XP = __ldg(reinterpret_cast<const float4*>(ac + xp));
-      const float4 YM = __ldg(reinterpret_cast<const float4*>(ac + ym));
-      const float4 YP = __ldg(reinterpret_cast<const float4*>(ac + yp));
-      const float zl = (k0 > 0) ? __ldg(ac - 1) : A[c].x;
-      const float zr = (k0 + 4 < Z) ? __ldg(ac + 4) : A[c].w;
-      float gx[4] = {0.5f * (XP.x - XM.x), 0.5f * (XP.y - XM.y), 0.5f * (XP.z - XM.z), 0.5f * (XP.w - XM.w)};
-      float gy[4] = {0.5f * (YP.x - YM.x), 0.5f * (YP.y - YM.y), 0.5f * (YP.z - YM.z), 0.5f * (YP.w - YM.w)};
-      float gz[4] = {0.5f * (A[c].y - zl), 0.5f * (A[c].z - A[c].x), 0.5f * (A[c].w - A[c].y), 0.5f * (zr - A[c].z)};
-      float o[4];
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        float g0 = gx[v], g1 = gy[v], g2 = gz[v];
+      for (int c = 0; c < 3; ++c) {
+        float g0 = 0.5f * (__ldg(ac[c] + xp) - __ldg(ac[c] + xm));
+        float g1 = 0.5f * (__ldg(ac[c] + yp) - __ldg(ac[c] + ym));
+        float g2 = 0.5f * (__ldg(ac[c] + zp) - __ldg(ac[c] + zm));
         if (c == 0) g0 += 1.f;
         if (c == 1) g1 += 1.f;
         if (c == 2) g2 += 1.f;
-        o[v] = g0 * val[0][v] + g1 * val[1][v] + g2 * val[2][v];  // diff.cu:118-120
+        on[c0 + c * V] = g0 * m0v + g1 * m1v + g2 * m2v;  // diff.cu:118-120
       }
-      *reinterpret_cast<float4*>(on + c * V + c0) = make_float4(o[0], o[1], o[2], o[3]);
     }
   }
 }
 
 static bool fast3_ok(const void* p0, const void* p1, const void* p2, int64_t N, const int64_t* sh) {
   if (((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15) return false;
-  if (sh[2] % 4 != 0 || sh[0] < 2 || sh[1] < 2 || sh[2] < 4) return false;
+  if (sh[0] < 2 || sh[1] < 2 || sh[2] < 2) return false;
   if (sh[0] * sh[1] * sh[2] >= (1LL << 31) / 4) return false;  // 32-bit offsets incl. channel stride
   if (N * sh[0] > 65535 || sh[1] > 8 * 65535LL) return false;
   return true;
@@ -166,7 +169,7 @@ static bool fast3_ok(const void* p0, const void* p1, const void* p2, int64_t N, 
 int Ad_star3_f32(void* out, const void* phi, const void* m, int64_t N, const int64_t* sh, cudaStream_t s) {
   if (!fast3_ok(out, phi, m, N, sh)) return LGM_EUNSUP;
   dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * sh[0])), block(32, 8);
-  gather3_kernel<0><<<grid, block, 0, s>>>((float*)out, (const float*)phi, (const float*)m, (int)sh[0],
+  gather3_kernel<0, 4><<<grid, block, 0, s>>>((float*)out, (const float*)phi, (const float*)m, (int)sh[0],
                                            (int)sh[1], (int)sh[2], 1.f, 0.f, 0.f, 0.f);
   count_launch("Ad_star", s);
   return finish(s, "lgm_Ad_star_fwd");
@@ -177,7 +180,7 @@ int compose3_f32(void* out, const void* u, const void* v, int64_t N, const int64
   if (!fast3_ok(out, u, v, N, sh)) return LGM_EUNSUP;
   const float dh = (float)ds, dl = (float)(ds - (double)dh);
   dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * sh[0])), block(32, 8);
-  gather3_kernel<1><<<grid, block, 0, s>>>((float*)out, (const float*)u, (const float*)v, (int)sh[0],
+  gather3_kernel<1, 4><<<grid, block, 0, s>>>((float*)out, (const float*)u, (const float*)v, (int)sh[0],
                                            (int)sh[1], (int)sh[2], dh, dl, (float)ds, (float)dt);
   count_launch("compose", s);
   return finish(s, "lgm_compose_fwd");
