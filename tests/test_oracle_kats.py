@@ -30,8 +30,8 @@ def test_interp_identity_shift_and_clamp(orc):
     u[:, 2] = 1.0  # integer shift along z with constant extension at the border
     out = orc.interp(I, u)
     assert torch.equal(out[..., :-1], I[..., 1:]) and torch.equal(out[..., -1], I[..., -1])
-    u[:, 2] = -2.3  # below range at k=0..2 -> v[0]
-    assert torch.equal(orc.interp(I, u)[..., 0], I[..., 0])
+    u[:, 2] = -2.3  # below range at k=0..2 -> both corners clamp to v[0]: (1-t)*v0 + t*v0, t = 0.7
+    assert torch.allclose(orc.interp(I, u)[..., 0], I[..., 0], rtol=1e-15, atol=1e-15)
     u[:, 2] = 50.0
     assert torch.equal(orc.interp(I, u)[..., 3], I[..., -1])
 
