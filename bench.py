@@ -112,10 +112,15 @@ def cpu_port_throughput(shape, batch, steps, reps=1):
 
 def run_reference(args):
     """The reference arm: the CPU port of the reference path, all host threads, same metric."""
-    import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; this arm is supposed to use every host core
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)
+    os.environ["MKL_NUM_THREADS"] = str(ncpu)
+    import torch
+    torch.set_num_threads(ncpu)
     batch, shape, nsteps = WORKLOADS[args.workload]
     sample_batch = 1
     V = shape[0] * shape[1] * shape[2]
@@ -228,9 +233,8 @@ def main():
         if with_e2e:
             h_host = torch.empty((batch, 3) + tuple(shape), dtype=torch.float32).pin_memory()
             def e2e_step():
-                md = m_host.to(dev, non_blocking=True)
-                hh = lm.expmap(metric, md, num_steps=nsteps)
-                h_host.copy_(hh, non_blocking=True)
+                # public host-buffer API: pipelined H2D / shoot / D2H over chunks of subjects
+                lm.expmap_host(metric, m_host, num_steps=nsteps, out=h_host, device=dev, chunk=4)
             for _ in range(min(W, 2)):
                 e2e_step()
             barrier()

@@ -11,7 +11,7 @@ from .diff import (jacobian_times_vectorfield, jacobian_times_vectorfield_adjoin
                    JacobianTimesVectorFieldFunction, JacobianTimesVectorFieldAdjointFunction)
 from .adjrep import ad, Ad, ad_star, Ad_star, coad, ad_dagger, Ad_dagger, sym, sym_dagger
 from .metric import FluidMetric, FluidMetricOperator, Metric, fluid_operator
-from .lddmm import expmap, expmap_advect, EPDiff_step, EPDiffStep, EPDiff_steps
+from .lddmm import expmap, expmap_advect, expmap_host, EPDiff_step, EPDiffStep, EPDiff_steps
 from .affine import (regrid, RegridFunction, RegridModule, affine_interp, AffineInterp,
                      AffineInterpFunction, affine_inverse, det_2x2)
 from .atlas import LDDMMAtlasBuilder, lddmm_atlas

@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblagomorph_b200.so")
+LIB_PATH = os.environ.get("LGM_LIB_PATH") or os.path.join(_HERE, "liblagomorph_b200.so")  # override: kernel experiments only
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int

@@ -125,9 +125,22 @@ __device__ __forceinline__ void reg_fft(C (&x)[RAD]) {
 
 // One in-place stage over blocks of BLOCK consecutive rows (BLOCK | N).
 // tw: table of N entries, tw[j] = e^{-2 pi i j / N}.
-template <typename R, int N, int BLOCK, int RAD, int L, bool INV>
+// Global-memory side of a stage: element (row r, line l) lives at g[r*grs + l] (lines are
+// consecutive words, so lanes running over l coalesce); lines l >= lvalid are padding.
+template <typename C>
+struct GSide {
+  C* g;
+  long long grs;
+  int lvalid;
+};
+
+// GSRC: the stage's inputs come from global memory instead of the tile; GDST: its outputs go to
+// global memory instead of the tile (used for the first / last stage of a pass, so the tile is
+// never filled or drained by a separate copy loop).
+template <typename R, int N, int BLOCK, int RAD, int L, bool INV, bool GSRC = false, bool GDST = false>
 __device__ __forceinline__ void fft_stage(typename Cx<R>::T* tile, int rs, int ls,
-                                          const typename Cx<R>::T* __restrict__ tw, int tid, int nth) {
+                                          const typename Cx<R>::T* __restrict__ tw, int tid, int nth,
+                                          GSide<typename Cx<R>::T> gs = GSide<typename Cx<R>::T>()) {
   using C = typename Cx<R>::T;
   constexpr int SUB = BLOCK / RAD;
   constexpr int ITEMS = L * (N / RAD);
@@ -135,29 +148,57 @@ __device__ __forceinline__ void fft_stage(typename Cx<R>::T* tile, int rs, int l
   for (int it = tid; it < ITEMS; it += nth) {
     const int l = it % L, q = it / L;
     const int blk = q / SUB, rest = q % SUB;
-    C* p = tile + (blk * BLOCK + rest) * rs + l * ls;
+    const int row0 = blk * BLOCK + rest;
+    C* p = tile + row0 * rs + l * ls;
+    C* gp = (GSRC || GDST) ? gs.g + (long long)row0 * gs.grs + l : nullptr;
+    const bool ok = !(GSRC || GDST) || l < gs.lvalid;
     C x[RAD];
     if (!INV) {
 #pragma unroll
-      for (int n = 0; n < RAD; ++n) x[n] = p[n * SUB * rs];
+      for (int n = 0; n < RAD; ++n) {
+        if (GSRC) {
+          C v;
+          v.x = v.y = R(0);
+          if (ok) v = gp[(long long)n * SUB * gs.grs];
+          x[n] = v;
+        } else {
+          x[n] = p[n * SUB * rs];
+        }
+      }
       reg_fft<RAD, false>(x);
 #pragma unroll
       for (int i = 0; i < RAD; ++i) {
         const int k = bitrev(i, BITS);
         C v = x[i];
         if (SUB > 1 && k != 0) v = cmul(v, tw[rest * k * (N / BLOCK)]);
-        p[k * SUB * rs] = v;
+        if (GDST) {
+          if (ok) gp[(long long)k * SUB * gs.grs] = v;
+        } else {
+          p[k * SUB * rs] = v;
+        }
       }
     } else {
 #pragma unroll
       for (int k = 0; k < RAD; ++k) {
-        C v = p[k * SUB * rs];
+        C v;
+        if (GSRC) {
+          v.x = v.y = R(0);
+          if (ok) v = gp[(long long)k * SUB * gs.grs];
+        } else {
+          v = p[k * SUB * rs];
+        }
         if (SUB > 1 && k != 0) v = cmulc(v, tw[rest * k * (N / BLOCK)]);
         x[k] = v;
       }
       reg_fft<RAD, true>(x);
 #pragma unroll
-      for (int i = 0; i < RAD; ++i) p[bitrev(i, BITS) * SUB * rs] = x[i];
+      for (int i = 0; i < RAD; ++i) {
+        if (GDST) {
+          if (ok) gp[(long long)bitrev(i, BITS) * SUB * gs.grs] = x[i];
+        } else {
+          p[bitrev(i, BITS) * SUB * rs] = x[i];
+        }
+      }
     }
   }
 }
@@ -230,6 +271,7 @@ template <typename R, int N, int BLOCK, int SI, int L>
 struct ColFFT {
   using C = typename Cx<R>::T;
   static constexpr int RAD = 1 << stage_bits(ilog2(N), SI);
+  static constexpr bool LASTSTAGE = (BLOCK / RAD == 1);
   static __device__ __forceinline__ void fwd(C* tile, int rs, int ls, const C* tw, int tid, int nth) {
     fft_stage<R, N, BLOCK, RAD, L, false>(tile, rs, ls, tw, tid, nth);
     if constexpr (BLOCK / RAD > 1) {
@@ -243,6 +285,52 @@ struct ColFFT {
       __syncthreads();
     }
     fft_stage<R, N, BLOCK, RAD, L, true>(tile, rs, ls, tw, tid, nth);
+  }
+  // variants whose first executed stage reads global memory (GIN) and/or whose last executed
+  // stage writes global memory (GOUT); gin / gout describe those arrays.
+  template <bool GIN, bool GOUT>
+  static __device__ __forceinline__ void fwd_g(C* tile, int rs, int ls, const C* tw, int tid, int nth,
+                                               GSide<C> gin, GSide<C> gout) {
+    constexpr bool first = (SI == 0);
+    if constexpr (first && GIN && LASTSTAGE && GOUT) {
+      // single-stage transform: global -> registers -> global (gin and gout may be the same array)
+      fft_stage<R, N, BLOCK, RAD, L, false, true, false>(tile, rs, ls, tw, tid, nth, gin);
+      __syncthreads();
+      for (int it = tid; it < L * N; it += nth) {
+        const int l = it % L, r = it / L;
+        if (l < gout.lvalid) gout.g[(long long)r * gout.grs + l] = tile[r * rs + l * ls];
+      }
+    } else {
+      fft_stage<R, N, BLOCK, RAD, L, false, first && GIN, LASTSTAGE && GOUT>(
+          tile, rs, ls, tw, tid, nth, (first && GIN) ? gin : gout);
+      if constexpr (!LASTSTAGE) {
+        __syncthreads();
+        ColFFT<R, N, BLOCK / RAD, SI + 1, L>::template fwd_g<GIN, GOUT>(tile, rs, ls, tw, tid, nth, gin, gout);
+      }
+    }
+  }
+  template <bool GIN, bool GOUT>
+  static __device__ __forceinline__ void inv_g(C* tile, int rs, int ls, const C* tw, int tid, int nth,
+                                               GSide<C> gin, GSide<C> gout) {
+    constexpr bool last = (SI == 0);  // executed last in the inverse
+    if constexpr (last && GOUT && LASTSTAGE && GIN) {
+      for (int it = tid; it < L * N; it += nth) {
+        const int l = it % L, r = it / L;
+        C v;
+        v.x = v.y = R(0);
+        if (l < gin.lvalid) v = gin.g[(long long)r * gin.grs + l];
+        tile[r * rs + l * ls] = v;
+      }
+      __syncthreads();
+      fft_stage<R, N, BLOCK, RAD, L, true, false, true>(tile, rs, ls, tw, tid, nth, gout);
+    } else {
+      if constexpr (!LASTSTAGE) {
+        ColFFT<R, N, BLOCK / RAD, SI + 1, L>::template inv_g<GIN, GOUT>(tile, rs, ls, tw, tid, nth, gin, gout);
+        __syncthreads();
+      }
+      fft_stage<R, N, BLOCK, RAD, L, true, LASTSTAGE && GIN, last && GOUT>(
+          tile, rs, ls, tw, tid, nth, (LASTSTAGE && GIN) ? gin : gout);
+    }
   }
 };
 

@@ -446,14 +446,9 @@ slab_fwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in,
     }
   }
   __syncthreads();
-  col_fft_fwd<R, Y, ZC>(tile, 1, P, twy, tid, kFftThreads);
-  __syncthreads();
-  C* o = spec + (size_t)blockIdx.x * Y * ZC;
-#pragma unroll 4
-  for (int idx = tid; idx < Y * ZC; idx += kFftThreads) {
-    const int ry = idx / ZC, rz = idx % ZC;
-    o[idx] = tile[rz * P + ry];
-  }
+  // Y transform; its last stage stores straight to the spectrum slab [ry][rz] (lanes over rz)
+  GSide<C> gout{spec + (size_t)blockIdx.x * Y * ZC, ZC, ZC};
+  ColFFT<R, Y, Y, 0, ZC>::template fwd_g<false, true>(tile, 1, P, twy, tid, kFftThreads, gout, gout);
 }
 
 // Slab inverse: mirror of slab_fwd_kernel (spectrum slab -> Y real lines), unnormalised.
@@ -472,14 +467,10 @@ slab_inv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec,
   for (int j = tid; j < Z; j += kFftThreads) twz[j] = twz_g[j];
   for (int j = tid; j < M; j += kFftThreads) twM[j] = twz_g[2 * j];
   for (int j = tid; j < Y; j += kFftThreads) twy[j] = twy_g[j];
-  const C* sp = spec + (size_t)blockIdx.x * Y * ZC;
-#pragma unroll 4
-  for (int idx = tid; idx < Y * ZC; idx += kFftThreads) {
-    const int ry = idx / ZC, rz = idx % ZC;
-    tile[rz * P + ry] = sp[idx];
-  }
   __syncthreads();
-  col_fft_inv<R, Y, ZC>(tile, 1, P, twy, tid, kFftThreads);
+  // inverse Y transform; its first stage loads straight from the spectrum slab [ry][rz]
+  GSide<C> gin{const_cast<C*>(spec) + (size_t)blockIdx.x * Y * ZC, ZC, ZC};
+  ColFFT<R, Y, Y, 0, ZC>::template inv_g<true, false>(tile, 1, P, twy, tid, kFftThreads, gin, gin);
   __syncthreads();
   for (int idx = tid; idx < Y * (M / 2 + 1); idx += kFftThreads) {
     const int l = idx % Y, k = idx / Y;
@@ -546,6 +537,26 @@ ypass_kernel(typename Cx<R>::T* __restrict__ spec, int X, int Zc,
     const int l = idx % T, r = idx / T;
     if (z0 + l < Zc) base[(long long)r * Zc + l] = tile[idx];
   }
+}
+
+// Y pass, second generation: same tiles, but the first stage reads global memory and the last
+// stage writes it (in place), so the tile is only the inter-stage exchange buffer.
+template <typename R, int NY, int T, bool INV>
+__global__ void __launch_bounds__(kFftThreads)
+ypass2_kernel(typename Cx<R>::T* __restrict__ spec, int X, int Zc,
+              const typename Cx<R>::T* __restrict__ tw_g) {
+  using C = typename Cx<R>::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* tile = reinterpret_cast<C*>(smem_raw);  // NY x T
+  C* tw = tile + NY * T;
+  const int tid = threadIdx.x;
+  for (int j = tid; j < NY; j += kFftThreads) tw[j] = tw_g[j];
+  const int z0 = blockIdx.x * T;
+  GSide<C> gs{spec + (((long long)blockIdx.z * X + blockIdx.y) * NY) * Zc + z0, Zc,
+              (Zc - z0 < T) ? (Zc - z0) : T};
+  __syncthreads();
+  if (!INV) ColFFT<R, NY, NY, 0, T>::template fwd_g<true, true>(tile, T, 1, tw, tid, kFftThreads, gs, gs);
+  else ColFFT<R, NY, NY, 0, T>::template inv_g<true, true>(tile, T, 1, tw, tid, kFftThreads, gs, gs);
 }
 
 // X pass with the multiplier: tiles of T consecutive words of the (Y x Zc) plane (contiguous
@@ -859,9 +870,9 @@ struct FastLaunch {
   template <int NY, bool INV>
   static int ypass(C* spec, int NC, int X, int Zc, const C* tw, cudaStream_t s) {
     const size_t smem = sizeof(C) * ((size_t)NY * T + NY);
-    LGM_CUDA_TRY(set_smem(ypass_kernel<R, NY, T, INV>, smem), "ypass smem");
+    LGM_CUDA_TRY(set_smem(ypass2_kernel<R, NY, T, INV>, smem), "ypass smem");
     dim3 grid((unsigned)cdiv(Zc, T), (unsigned)X, (unsigned)NC);
-    ypass_kernel<R, NY, T, INV><<<grid, kFftThreads, smem, s>>>(spec, X, Zc, tw);
+    ypass2_kernel<R, NY, T, INV><<<grid, kFftThreads, smem, s>>>(spec, X, Zc, tw);
     count_launch("ypass", s);
     return LGM_OK;
   }

@@ -144,3 +144,62 @@ def expmap(metric, m0, T=1.0, num_steps=10, phiinv=None, mommask=None, checkpoin
                 phiinv = EPDiff_step(metric, m0, dt, phiinv, mommask=mommask)
         done += k
     return phiinv
+
+
+def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chunk=4):
+    """Shoot momenta that live in (pinned) HOST memory and return the deformations in host memory.
+
+    Subjects are independent, so the batch is cut into chunks that flow through a three-stage
+    pipeline on separate CUDA streams: host->device copy of chunk i+1, EPDiff shoot of chunk i,
+    device->host copy of chunk i-1 all overlap (PCIe is full duplex). Same result as
+    `expmap(metric, m0_host.cuda(), ...).cpu()`. No autograd.
+    """
+    if m0_host.is_cuda:
+        raise RuntimeError("expmap_host takes host tensors; use expmap for device tensors")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    N = m0_host.shape[0]
+    if out is None:
+        out = torch.empty_like(m0_host, pin_memory=True)
+    if N == 0:
+        return out
+    chunk = max(1, min(int(chunk), N))
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
+    nbuf = 3
+    dbuf = [torch.empty((chunk,) + tuple(m0_host.shape[1:]), dtype=m0_host.dtype, device=dev) for _ in range(nbuf)]
+    in_done = [torch.cuda.Event() for _ in range(nbuf)]
+    out_done = [None] * nbuf   # result buffer of slot b has been copied out
+    comp_done = [None] * nbuf  # input buffer of slot b has been consumed
+    results = []
+    starts = list(range(0, N, chunk))
+
+    def issue_h2d(ci):
+        b = ci % nbuf
+        n = min(chunk, N - starts[ci])
+        with torch.cuda.stream(s_in):
+            if comp_done[b] is not None:
+                s_in.wait_event(comp_done[b])
+            dbuf[b][:n].copy_(m0_host[starts[ci]:starts[ci] + n], non_blocking=True)
+            in_done[b].record(s_in)
+
+    issue_h2d(0)
+    for ci, st in enumerate(starts):
+        b = ci % nbuf
+        n = min(chunk, N - st)
+        if ci + 1 < len(starts):
+            issue_h2d(ci + 1)
+        cur.wait_event(in_done[b])
+        with torch.no_grad():
+            h = expmap(metric, dbuf[b][:n], T=T, num_steps=num_steps)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        comp_done[b] = ev
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev)
+            out[st:st + n].copy_(h, non_blocking=True)
+            h.record_stream(s_out)
+    cur.wait_stream(s_out)
+    cur.wait_stream(s_in)
+    return out

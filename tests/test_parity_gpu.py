@@ -231,3 +231,15 @@ def test_debug_mode_and_launch_count(lm):
     lm.interp(x, x)
     assert lm.launch_count() == n0 + 1
     lm.set_debug_mode(False)
+
+
+def test_expmap_host_pipeline(lm, orc):
+    """host-buffer API (chunked, three streams) == plain device shoot, incl. a ragged last chunk"""
+    params = [0.1, 0.0, 0.01]
+    gm = lm.FluidMetric(params)
+    m0 = smooth_field((5, 3, 16, 16, 16), torch.float32, 72, amp=1.0, sigma=2.0)
+    m0 = (m0 * (3.0 / orc.FluidMetric(params).sharp(m0).abs().max())).pin_memory()
+    ref = lm.expmap(gm, m0.cuda(), num_steps=3).cpu()
+    out = lm.expmap_host(gm, m0, num_steps=3, chunk=2)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
