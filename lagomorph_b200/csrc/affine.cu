@@ -227,6 +227,7 @@ extern "C" int lgm_affine_interp_fwd(int dtype, void* out, const void* I, const 
                                      const int64_t* shape, void* stream) {
   LGM_REQUIRE(dim == 2 || dim == 3, "Only two- and three-dimensional affine interpolation is supported");
   LGM_REQUIRE(N >= 0 && N <= 65535 && (NI == N || NI == 1), "lgm_affine_interp_fwd: bad batch sizes");
+  LGM_REQUIRE(dim == 2 ? geom_fits<2>(shape) : geom_fits<3>(shape), "lgm_affine_interp_fwd: volume too large");
   DISPATCH_RD(dtype, dim, affine_fwd_t, out, I, A, T, N, NI, C, shape, (cudaStream_t)stream);
 }
 extern "C" int lgm_affine_interp_bwd(int dtype, void* d_I, void* d_A, void* d_T, const void* gout,
@@ -235,5 +236,6 @@ extern "C" int lgm_affine_interp_bwd(int dtype, void* d_I, void* d_A, void* d_T,
                                      void* stream) {
   LGM_REQUIRE(dim == 2 || dim == 3, "Only two- and three-dimensional affine interpolation is supported");
   LGM_REQUIRE(N >= 0 && N <= 65535 && (NI == N || NI == 1), "lgm_affine_interp_bwd: bad batch sizes");
+  LGM_REQUIRE(dim == 2 ? geom_fits<2>(shape) : geom_fits<3>(shape), "lgm_affine_interp_bwd: volume too large");
   DISPATCH_RD(dtype, dim, affine_bwd_t, d_I, d_A, d_T, gout, I, A, T, N, NI, C, shape, (cudaStream_t)stream);
 }

@@ -18,10 +18,12 @@ bool debug_mode();
   } while (0)
 
 // Spatial geometry of one tensor: extents and element strides, last axis fastest.
+// One (sample, channel) volume is limited to 2^31-1 voxels so that all in-volume index
+// arithmetic is 32-bit (batch / channel offsets stay 64-bit).
 template <int D>
 struct Geom {
   int n[D];
-  long long st[D];
+  int st[D];
   long long V;
 };
 
@@ -31,11 +33,22 @@ inline Geom<D> make_geom(const int64_t* shape) {
   long long s = 1;
   for (int a = D - 1; a >= 0; --a) {
     g.n[a] = (int)shape[a];
-    g.st[a] = s;
+    g.st[a] = (int)s;
     s *= shape[a];
   }
   g.V = s;
   return g;
+}
+
+template <int D>
+inline bool geom_fits(const int64_t* shape) {
+  long long s = 1;
+  for (int a = 0; a < D; ++a) {
+    if (shape[a] < 0 || shape[a] > 0x7fffffff) return false;
+    s *= shape[a];
+    if (s > 0x7fffffffLL) return false;
+  }
+  return true;
 }
 
 __host__ __device__ inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
@@ -136,11 +149,12 @@ __device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); 
 
 // Decode a linear voxel id into per-axis positions.
 template <int D>
-__device__ __forceinline__ void decode(long long vid, const Geom<D>& g, int (&pos)[D]) {
+__device__ __forceinline__ void decode(long long vid64, const Geom<D>& g, int (&pos)[D]) {
+  unsigned vid = (unsigned)vid64;  // < 2^31 by construction (geom_fits)
 #pragma unroll
   for (int a = D - 1; a > 0; --a) {
-    long long q = vid / g.n[a];
-    pos[a] = (int)(vid - q * g.n[a]);
+    unsigned q = vid / (unsigned)g.n[a];
+    pos[a] = (int)(vid - q * (unsigned)g.n[a]);
     vid = q;
   }
   pos[0] = (int)vid;

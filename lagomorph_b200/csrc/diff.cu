@@ -473,7 +473,10 @@ using namespace lgm;
     return set_error(LGM_EINVAL, "unsupported dtype %d / dim %d", (dtype), (dim)); \
   } while (0)
 
-#define CHECK_N(N) LGM_REQUIRE((N) >= 0 && (N) <= 65535, "batch size out of range")
+#define CHECK_N(N)                                                                                     \
+  LGM_REQUIRE((N) >= 0 && (N) <= 65535, "batch size out of range");                                    \
+  LGM_REQUIRE((dim == 2 && geom_fits<2>(shape)) || (dim == 3 && geom_fits<3>(shape)),                  \
+              "Only two- and three-dimensional fields of fewer than 2^31 voxels are supported")
 
 extern "C" int lgm_jtvf_fwd(int dtype, void* out, const void* v, const void* w, int64_t N,
                             int64_t C, int dim, const int64_t* shape, int displacement,

@@ -880,7 +880,7 @@ struct FastLaunch {
   static int xpass1(C* spec, long long N, long long plane, int Zc, const FluidPlan& p, double alpha,
                     double beta, double gamma, R scale, cudaStream_t s) {
     // tile width: 32 words (256 B runs) while the tile stays small, else the class default
-    constexpr int TX = (sizeof(R) == 4 && NCH * NX <= 128) ? 32 : T;
+    constexpr int TX = (sizeof(R) == 4 && NCH * NX <= 128) ? 32 : T;  // 32 at NX=256 measured slower (regs)
     const size_t smem = sizeof(C) * ((size_t)NCH * NX * TX + NX) + sizeof(R) * 2 * NX;
     LGM_CUDA_TRY(set_smem(xpass2_kernel<R, NX, TX, D, NCH, INVERSE>, smem), "xpass smem");
     dim3 grid((unsigned)cdiv(plane, TX), (unsigned)(NCH == 1 ? N * D : N));
@@ -1142,6 +1142,7 @@ extern "C" int lgm_fluid_apply(int dtype, void* out, const void* in, int64_t N, 
                                double gamma, void* workspace, int64_t workspace_bytes, void* stream) {
   LGM_REQUIRE(dim == 2 || dim == 3, "Only two- and three-dimensional fluid metric is supported");
   LGM_REQUIRE(N >= 0 && N <= 21845, "lgm_fluid_apply: batch size out of range");
+  LGM_REQUIRE(dim == 2 ? geom_fits<2>(shape) : geom_fits<3>(shape), "lgm_fluid_apply: volume too large");
   if (dtype == LGM_F32)
     return fluid_apply_t<float>(out, in, N, dim, shape, inverse, alpha, beta, gamma, workspace, workspace_bytes, (cudaStream_t)stream);
   if (dtype == LGM_F64)

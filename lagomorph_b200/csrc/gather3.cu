@@ -15,6 +15,10 @@
 // instructions; floor() is a magic-number add.
 #include "common.cuh"
 
+#ifndef LGM_GATHER_BX
+#define LGM_GATHER_BX 1  /* 2,4,8 measured equal on B200: the gathers are L1-data-pipe bound, not L2 bound */
+#endif
+
 namespace lgm {
 
 // RN_f32(fi + d*u) for d = dh + dl (double split in two floats), product and sum carried as
@@ -83,14 +87,17 @@ __device__ __forceinline__ void z_pair(const Ax3& az, int Z, int& zs, float& v) 
 
 // MODE 0: Ad_star (a = phiinv, b = m0); MODE 1: compose (a = u, b = v).
 // blockDim = (32, 8): a warp walks one z row (lane = z, NV chunks of 32), a CTA covers 8 y rows.
-template <int MODE, int NV>
+template <int MODE, int NV, int BX>
 __global__ void __launch_bounds__(256)
 gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
                int X, int Y, int Z, float dh, float dl, float dsr, float dtr) {
-  const int j = blockIdx.y * 8 + threadIdx.y;
-  if (j >= Y) return;
-  const int i = blockIdx.z % X;
-  const int n = blockIdx.z / X;
+  // blockDim = (32, 8/BX, BX): BX neighbouring x slabs share a CTA so that the upper-x corner rows
+  // of one slab are the lower-x rows of the next (L1 reuse instead of a second L2 fetch)
+  const int j = blockIdx.y * (8 / BX) + threadIdx.y;
+  const int XB = (X + BX - 1) / BX;
+  const int i = (blockIdx.z % XB) * BX + threadIdx.z;
+  if (j >= Y || i >= X) return;
+  const int n = blockIdx.z / XB;
   const int sy = Z, sx = Y * Z;
   const int V = X * sx;
   const float* an = a + (size_t)n * 3 * V;
@@ -161,15 +168,16 @@ static bool fast3_ok(const void* p0, const void* p1, const void* p2, int64_t N, 
   if (((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15) return false;
   if (sh[0] < 2 || sh[1] < 2 || sh[2] < 2) return false;
   if (sh[0] * sh[1] * sh[2] >= (1LL << 31) / 4) return false;  // 32-bit offsets incl. channel stride
-  if (N * sh[0] > 65535 || sh[1] > 8 * 65535LL) return false;
+  if (N * sh[0] > 65535 || sh[1] > 65535LL) return false;
   return true;
 }
 
 // returns LGM_EUNSUP when the fast path does not apply (caller falls back to the generic kernel)
 int Ad_star3_f32(void* out, const void* phi, const void* m, int64_t N, const int64_t* sh, cudaStream_t s) {
   if (!fast3_ok(out, phi, m, N, sh)) return LGM_EUNSUP;
-  dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * sh[0])), block(32, 8);
-  gather3_kernel<0, 4><<<grid, block, 0, s>>>((float*)out, (const float*)phi, (const float*)m, (int)sh[0],
+  constexpr int BX = LGM_GATHER_BX;
+  dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8 / BX), (unsigned)(N * cdiv(sh[0], BX))), block(32, 8 / BX, BX);
+  gather3_kernel<0, 4, BX><<<grid, block, 0, s>>>((float*)out, (const float*)phi, (const float*)m, (int)sh[0],
                                            (int)sh[1], (int)sh[2], 1.f, 0.f, 0.f, 0.f);
   count_launch("Ad_star", s);
   return finish(s, "lgm_Ad_star_fwd");
@@ -179,8 +187,9 @@ int compose3_f32(void* out, const void* u, const void* v, int64_t N, const int64
                  cudaStream_t s) {
   if (!fast3_ok(out, u, v, N, sh)) return LGM_EUNSUP;
   const float dh = (float)ds, dl = (float)(ds - (double)dh);
-  dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * sh[0])), block(32, 8);
-  gather3_kernel<1, 4><<<grid, block, 0, s>>>((float*)out, (const float*)u, (const float*)v, (int)sh[0],
+  constexpr int BX = LGM_GATHER_BX;
+  dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8 / BX), (unsigned)(N * cdiv(sh[0], BX))), block(32, 8 / BX, BX);
+  gather3_kernel<1, 4, BX><<<grid, block, 0, s>>>((float*)out, (const float*)u, (const float*)v, (int)sh[0],
                                            (int)sh[1], (int)sh[2], dh, dl, (float)ds, (float)dt);
   count_launch("compose", s);
   return finish(s, "lgm_compose_fwd");

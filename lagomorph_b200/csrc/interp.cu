@@ -289,6 +289,7 @@ static bool shape_ok(int dim, const int64_t* shape) {
   for (int a = 0; a < dim; ++a) {
     if (shape[a] < 0 || shape[a] > 0x7fffffff) return false;
     v *= shape[a];
+    if (v > 0x7fffffffLL) return false;  // 32-bit in-volume indexing
   }
   return v >= 0;
 }
