@@ -39,10 +39,13 @@ __device__ __forceinline__ R cdiffT(const R* __restrict__ p, const R* __restrict
 }
 
 // ---------------------------------------------------------------- jtvf forward
-template <typename R, int D, bool DISP, bool TRANS>
+// CC: compile-time channel count (0 = use the runtime C); the common C == D case is unrolled so the
+// loads of w and of the stencil legs are hoisted and batched.
+template <typename R, int D, bool DISP, bool TRANS, int CC = 0>
 __global__ void __launch_bounds__(kThreads)
 jtvf_fwd_kernel(R* __restrict__ out, const R* __restrict__ v, const R* __restrict__ w, Geom<D> g,
-                int C) {
+                int C_rt) {
+  const int C = CC ? CC : C_rt;
   const long long vid = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (vid >= g.V) return;
   const long long n = blockIdx.y;
@@ -67,6 +70,7 @@ jtvf_fwd_kernel(R* __restrict__ out, const R* __restrict__ v, const R* __restric
 #pragma unroll
     for (int d = 0; d < D; ++d) on[d * g.V] = acc[d];
   } else {  // cuda/diff.cu:46-56, :104-122
+#pragma unroll
     for (int c = 0; c < C; ++c) {
       R gr[D];
       grad<R, D>(vn + c * g.V, pos, g, gr);
@@ -83,10 +87,11 @@ jtvf_fwd_kernel(R* __restrict__ out, const R* __restrict__ v, const R* __restric
 }
 
 // ---------------------------------------------------------------- jtvf backward
-template <typename R, int D, bool DISP, bool TRANS, bool NEED_V, bool NEED_W>
+template <typename R, int D, bool DISP, bool TRANS, bool NEED_V, bool NEED_W, int CC = 0>
 __global__ void __launch_bounds__(kThreads)
 jtvf_bwd_kernel(R* __restrict__ d_v, R* __restrict__ d_w, const R* __restrict__ go,
-                const R* __restrict__ v, const R* __restrict__ w, Geom<D> g, int C) {
+                const R* __restrict__ v, const R* __restrict__ w, Geom<D> g, int C_rt) {
+  const int C = CC ? CC : C_rt;
   const long long vid = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (vid >= g.V) return;
   const long long n = blockIdx.y;
@@ -124,6 +129,7 @@ jtvf_bwd_kernel(R* __restrict__ d_v, R* __restrict__ d_w, const R* __restrict__ 
     R dw[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) dw[d] = R(0);
+#pragma unroll
     for (int c = 0; c < C; ++c) {
       if (NEED_W) {  // d_w[d] += (D_d v_c + delta) gout_c   (diff.cu:417-431)
         R gr[D];
@@ -153,16 +159,18 @@ jtvf_bwd_kernel(R* __restrict__ d_v, R* __restrict__ d_w, const R* __restrict__ 
 }
 
 // ---------------------------------------------------------------- adjoint fwd / bwd
-template <typename R, int D>
+template <typename R, int D, int CC = 0>
 __global__ void __launch_bounds__(kThreads)
 jtvf_adj_fwd_kernel(R* __restrict__ out, const R* __restrict__ z, const R* __restrict__ w,
-                    Geom<D> g, int C) {
+                    Geom<D> g, int C_rt) {
+  const int C = CC ? CC : C_rt;
   const long long vid = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (vid >= g.V) return;
   const long long n = blockIdx.y;
   int pos[D];
   decode<D>(vid, g, pos);
   const R* wn = w + n * D * g.V + vid;
+#pragma unroll
   for (int c = 0; c < C; ++c) {  // out_c = sum_d D_d^T (w_d z_c)   (diff.cu:546-632)
     const R* zc = z + (n * C + c) * g.V + vid;
     R acc = R(0);
@@ -351,7 +359,11 @@ static int jtvf_fwd_t(void* out, const void* v, const void* w, int64_t N, int64_
   Geom<D> g = make_geom<D>(shape);
   if (N == 0 || C == 0) return LGM_OK;
   dim3 grid((unsigned)cdiv(g.V, kThreads), (unsigned)N);
-#define L(DI, TR) jtvf_fwd_kernel<R, D, DI, TR><<<grid, kThreads, 0, s>>>((R*)out, (const R*)v, (const R*)w, g, (int)C)
+#define L(DI, TR)                                                                                              \
+  do {                                                                                                         \
+    if (C == D) jtvf_fwd_kernel<R, D, DI, TR, D><<<grid, kThreads, 0, s>>>((R*)out, (const R*)v, (const R*)w, g, (int)C); \
+    else jtvf_fwd_kernel<R, D, DI, TR, 0><<<grid, kThreads, 0, s>>>((R*)out, (const R*)v, (const R*)w, g, (int)C);        \
+  } while (0)
   if (disp && trans) L(true, true);
   else if (disp) L(true, false);
   else if (trans) L(false, true);
@@ -364,7 +376,11 @@ static int jtvf_fwd_t(void* out, const void* v, const void* w, int64_t N, int64_
 template <typename R, int D, bool DI, bool TR>
 static void jtvf_bwd_launch(dim3 grid, cudaStream_t s, void* d_v, void* d_w, const void* go,
                             const void* v, const void* w, const Geom<D>& g, int C) {
-#define L(NV, NW) jtvf_bwd_kernel<R, D, DI, TR, NV, NW><<<grid, kThreads, 0, s>>>((R*)d_v, (R*)d_w, (const R*)go, (const R*)v, (const R*)w, g, C)
+#define L(NV, NW)                                                                                              \
+  do {                                                                                                         \
+    if (C == D) jtvf_bwd_kernel<R, D, DI, TR, NV, NW, D><<<grid, kThreads, 0, s>>>((R*)d_v, (R*)d_w, (const R*)go, (const R*)v, (const R*)w, g, C); \
+    else jtvf_bwd_kernel<R, D, DI, TR, NV, NW, 0><<<grid, kThreads, 0, s>>>((R*)d_v, (R*)d_w, (const R*)go, (const R*)v, (const R*)w, g, C);        \
+  } while (0)
   if (d_v && d_w) L(true, true);
   else if (d_v) L(true, false);
   else L(false, true);
@@ -395,7 +411,8 @@ static int jtvf_adj_fwd_t(void* out, const void* z, const void* w, int64_t N, in
   Geom<D> g = make_geom<D>(shape);
   if (N == 0 || C == 0) return LGM_OK;
   dim3 grid((unsigned)cdiv(g.V, kThreads), (unsigned)N);
-  jtvf_adj_fwd_kernel<R, D><<<grid, kThreads, 0, s>>>((R*)out, (const R*)z, (const R*)w, g, (int)C);
+  if (C == D) jtvf_adj_fwd_kernel<R, D, D><<<grid, kThreads, 0, s>>>((R*)out, (const R*)z, (const R*)w, g, (int)C);
+  else jtvf_adj_fwd_kernel<R, D, 0><<<grid, kThreads, 0, s>>>((R*)out, (const R*)z, (const R*)w, g, (int)C);
   count_launch("jtvf_adj_fwd", s);
   return finish(s, "lgm_jtvf_adj_fwd");
 }

@@ -2,15 +2,15 @@
 //   Ad_star : out_c = sum_d (D_d phi_c + delta_cd) * m_d(x + phi(x))          (adjrep.py:86-97)
 //   compose : out_c = ds*u_c + dt*v_c(x + ds*u(x))                            (deform.py:53-55)
 //
-// Layout of the work: a thread owns 4 consecutive voxels along z (one float4 of every channel),
-// a warp one 128-voxel z segment, a CTA 8 neighbouring y rows of one x slab, so that
-//   - every direct load / store is a 16-byte vector, the Jacobian's y/x neighbours are float4
-//     loads of adjacent rows (L1 hits across the CTA's rows) and its z neighbours come from the
-//     thread's own vector plus two scalars;
-//   - the 8-corner gathers of a warp land on runs of consecutive addresses for smooth flows
-//     (served by L1/L2, the 24 scalar loads per voxel are the floor of this formulation);
-//   - all index arithmetic is 32-bit, with no division in the hot loop.
-// Sample coordinates reproduce the reference's "form in double, round to float"
+// Layout of the work: lane = z. A warp walks one 128-voxel z row in 4 chunks of 32, a CTA covers 8
+// neighbouring y rows of one x slab, the batch and x are the grid's z dimension, so that
+//   - every direct load / store of a warp is one aligned 128-byte row segment;
+//   - the 8-corner gathers of a warp land on runs of consecutive addresses for smooth flows (two
+//     cache lines per request); the upper-z corner is the +1 neighbour of the lower one, i.e. an
+//     immediate offset on the same address register;
+//   - all index arithmetic is 32-bit, one IMAD.WIDE per corner row, no division in the hot loop.
+// (A float4-per-thread mapping was measured and rejected: it quadruples the L1 wavefronts of every
+// gather request.) Sample coordinates reproduce the reference's "form in double, round to float"
 // (cuda/interp.cu:68-73) with error-free float transformations instead of fp64/conversion
 // instructions; floor() is a magic-number add.
 #include "common.cuh"
@@ -164,8 +164,131 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
   }
 }
 
+// Plain interp (cuda/interp.cu:47-78), any channel count, optional broadcast image: same thread
+// mapping and corner-pair gather as above, weights computed once per voxel for all channels.
+template <int NV, bool UNIT_DT>
+__global__ void __launch_bounds__(256)
+interp3_kernel(float* __restrict__ out, const float* __restrict__ I, const float* __restrict__ u, int X,
+               int Y, int Z, int C, size_t I_batch_stride, float dh, float dl) {
+  const int j = blockIdx.y * 8 + threadIdx.y;
+  if (j >= Y) return;
+  const int i = blockIdx.z % X;
+  const int n = blockIdx.z / X;
+  const int sy = Z, sx = Y * Z;
+  const int V = X * sx;
+  const float* un = u + (size_t)n * 3 * V;
+  const float* In = I + (size_t)n * I_batch_stride;
+  float* on = out + (size_t)n * C * V;
+  asm volatile("" : "+l"(In));
+  const int row = i * sx + j * sy;
+  const float fi = (float)i, fj = (float)j;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int k = (blockIdx.x * NV + v) * 32 + threadIdx.x;
+    if (k >= Z) break;
+    const int c0 = row + k;
+    const float A0 = __ldg(un + c0), A1 = __ldg(un + c0 + V), A2 = __ldg(un + c0 + 2 * V);
+    float hx, hy, hz;
+    const float fk = (float)k;
+    if (UNIT_DT) {
+      hx = __fadd_rn(fi, A0);
+      hy = __fadd_rn(fj, A1);
+      hz = __fadd_rn(fk, A2);
+    } else {
+      hx = coord_f32(fi, A0, dh, dl);
+      hy = coord_f32(fj, A1, dh, dl);
+      hz = coord_f32(fk, A2, dh, dl);
+    }
+    const Ax3 ax = axis_fast(hx, X), ay = axis_fast(hy, Y), az = axis_fast(hz, Z);
+    int zs;
+    float wv;
+    z_pair(az, Z, zs, wv);
+    const unsigned rx0 = ax.i0 * sx + zs, rx1 = ax.i1 * sx + zs;
+    const unsigned ry0 = ay.i0 * sy, ry1 = ay.i1 * sy;
+    const unsigned i00 = rx0 + ry0, i01 = rx0 + ry1, i10 = rx1 + ry0, i11 = rx1 + ry1;
+    const float omt = 1.f - ax.t, omu = 1.f - ay.t, omv = 1.f - wv;
+    const float* Ic = In;
+    float* oc = on + c0;
+    for (int c = 0; c < C; ++c, Ic += V, oc += V)
+      *oc = trilerp(Ic, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv);
+  }
+}
+
+// Adjoint of interp (splat, cuda/interp.cu:185-244 d_I part): every voxel adds w_corner * gout to
+// its 8 corner voxels. Lanes are consecutive in z, so for smooth flows the upper-z corner of lane L
+// is the lower-z corner of lane L+1: those two contributions are merged with one warp shuffle and
+// leave as ONE red.global.add, which halves the L2 atomic traffic (the limiter of this kernel).
+// Corner weights follow the reference's alternating "d = 1 - d" sequence (include/interp.h:437-453).
+template <int NV, bool UNIT_DT>
+__global__ void __launch_bounds__(256)
+splat3_kernel(float* __restrict__ d_I, const float* __restrict__ go, const float* __restrict__ u, int X,
+              int Y, int Z, int C, size_t I_batch_stride, float dh, float dl) {
+  const int j = blockIdx.y * 8 + threadIdx.y;
+  if (j >= Y) return;  // warp-uniform (a warp is one row)
+  const int i = blockIdx.z % X;
+  const int n = blockIdx.z / X;
+  const int sy = Z, sx = Y * Z;
+  const int V = X * sx;
+  const float* un = u + (size_t)n * 3 * V;
+  const float* gn = go + (size_t)n * C * V;
+  float* dn = d_I + (size_t)n * I_batch_stride;
+  const int row = i * sx + j * sy;
+  const float fi = (float)i, fj = (float)j;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x;
+#pragma unroll 1
+  for (int v = 0; v < NV; ++v) {
+    const int k = (blockIdx.x * NV + v) * 32 + lane;
+    if ((blockIdx.x * NV + v) * 32 >= Z) break;  // whole chunk out of range (Z % 32 == 0)
+    const int c0 = row + k;
+    const float A0 = __ldg(un + c0), A1 = __ldg(un + c0 + V), A2 = __ldg(un + c0 + 2 * V);
+    float hx, hy, hz;
+    const float fk = (float)k;
+    if (UNIT_DT) {
+      hx = __fadd_rn(fi, A0);
+      hy = __fadd_rn(fj, A1);
+      hz = __fadd_rn(fk, A2);
+    } else {
+      hx = coord_f32(fi, A0, dh, dl);
+      hy = coord_f32(fj, A1, dh, dl);
+      hz = coord_f32(fk, A2, dh, dl);
+    }
+    const Ax3 ax = axis_fast(hx, X), ay = axis_fast(hy, Y), az = axis_fast(hz, Z);
+    // weight sequences: w0 = 1-t, then alternately 1-w
+    const float wx0 = 1.f - ax.t, wx1 = 1.f - wx0;
+    const float wy0 = 1.f - ay.t, wy1 = 1.f - wy0, wy2 = 1.f - wy1, wy3 = 1.f - wy2;
+    const float wz0 = 1.f - az.t, wz1 = 1.f - wz0, wz2 = 1.f - wz1, wz3 = 1.f - wz2;
+    const float wr[4] = {wx0 * wy0, wx0 * wy1, wx1 * wy2, wx1 * wy3};  // rows (x0,y0),(x0,y1),(x1,y0),(x1,y1)
+    const float wlo[4] = {wr[0] * wz0, wr[1] * wz2, wr[2] * wz2, wr[3] * wz2};
+    const float whi[4] = {wr[0] * wz1, wr[1] * wz3, wr[2] * wz3, wr[3] * wz3};
+    const unsigned rb[4] = {(unsigned)(ax.i0 * sx + ay.i0 * sy), (unsigned)(ax.i0 * sx + ay.i1 * sy),
+                            (unsigned)(ax.i1 * sx + ay.i0 * sy), (unsigned)(ax.i1 * sx + ay.i1 * sy)};
+    bool give[4], took[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const unsigned alo = rb[r] + az.i0, ahi = rb[r] + az.i1;
+      const unsigned nxt = __shfl_down_sync(full, alo, 1);
+      give[r] = (lane < 31) && (nxt == ahi) && (ahi != alo);
+      took[r] = __shfl_up_sync(full, (int)give[r], 1) != 0 && lane > 0;
+    }
+    for (int c = 0; c < C; ++c) {
+      const float d = __ldg(gn + (size_t)c * V + c0);
+      float* dc = dn + (size_t)c * V;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float vlo = wlo[r] * d;
+        const float vhi = whi[r] * d;
+        const float recv = __shfl_up_sync(full, give[r] ? vhi : 0.f, 1);
+        if (took[r]) vlo += recv;
+        atomicAdd(dc + rb[r] + az.i0, vlo);
+        if (!give[r]) atomicAdd(dc + rb[r] + az.i1, vhi);
+      }
+    }
+  }
+}
+
 static bool fast3_ok(const void* p0, const void* p1, const void* p2, int64_t N, const int64_t* sh) {
-  if (((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15) return false;
+  (void)p0; (void)p1; (void)p2;  // scalar accesses: no alignment requirement beyond the element
   if (sh[0] < 2 || sh[1] < 2 || sh[2] < 2) return false;
   if (sh[0] * sh[1] * sh[2] >= (1LL << 31) / 4) return false;  // 32-bit offsets incl. channel stride
   if (N * sh[0] > 65535 || sh[1] > 65535LL) return false;
@@ -193,6 +316,42 @@ int compose3_f32(void* out, const void* u, const void* v, int64_t N, const int64
                                            (int)sh[1], (int)sh[2], dh, dl, (float)ds, (float)dt);
   count_launch("compose", s);
   return finish(s, "lgm_compose_fwd");
+}
+
+int interp3_f32(void* out, const void* I, const void* u, int64_t N, int64_t NI, int64_t C, const int64_t* sh,
+                double dt, cudaStream_t s) {
+  if (!fast3_ok(out, I, u, N, sh) || C < 1 || C > 0x7fffffff / (sh[0] * sh[1] * sh[2])) return LGM_EUNSUP;
+  const size_t ibs = (NI < N) ? 0 : (size_t)C * sh[0] * sh[1] * sh[2];
+  dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * sh[0])), block(32, 8);
+  if (dt == 1.0) {
+    interp3_kernel<4, true><<<grid, block, 0, s>>>((float*)out, (const float*)I, (const float*)u, (int)sh[0],
+                                                   (int)sh[1], (int)sh[2], (int)C, ibs, 1.f, 0.f);
+  } else {
+    const float dh = (float)dt, dl = (float)(dt - (double)dh);
+    interp3_kernel<4, false><<<grid, block, 0, s>>>((float*)out, (const float*)I, (const float*)u, (int)sh[0],
+                                                    (int)sh[1], (int)sh[2], (int)C, ibs, dh, dl);
+  }
+  count_launch("interp_fwd", s);
+  return finish(s, "lgm_interp_fwd");
+}
+
+// d_I must be zero-filled by the caller. LGM_EUNSUP when the fast path does not apply.
+int splat3_f32(void* d_I, const void* go, const void* u, int64_t N, int64_t NI, int64_t C, const int64_t* sh,
+               double dt, cudaStream_t s) {
+  if (!fast3_ok(d_I, go, u, N, sh) || sh[2] % 32 != 0 || C < 1 || C > 0x7fffffff / (sh[0] * sh[1] * sh[2]))
+    return LGM_EUNSUP;
+  const size_t ibs = (NI < N) ? 0 : (size_t)C * sh[0] * sh[1] * sh[2];
+  dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * sh[0])), block(32, 8);
+  if (dt == 1.0) {
+    splat3_kernel<4, true><<<grid, block, 0, s>>>((float*)d_I, (const float*)go, (const float*)u, (int)sh[0],
+                                                  (int)sh[1], (int)sh[2], (int)C, ibs, 1.f, 0.f);
+  } else {
+    const float dh = (float)dt, dl = (float)(dt - (double)dh);
+    splat3_kernel<4, false><<<grid, block, 0, s>>>((float*)d_I, (const float*)go, (const float*)u, (int)sh[0],
+                                                   (int)sh[1], (int)sh[2], (int)C, ibs, dh, dl);
+  }
+  count_launch("interp_splat", s);
+  return finish(s, "lgm_interp_bwd");
 }
 
 }  // namespace lgm

@@ -272,6 +272,13 @@ static int regrid_t(void* dst, const void* src, int64_t N, int64_t C, const int6
 
 }  // namespace lgm
 
+namespace lgm {  // gather3.cu; LGM_EUNSUP = fast path not applicable
+int interp3_f32(void* out, const void* I, const void* u, int64_t N, int64_t NI, int64_t C, const int64_t* sh,
+                double dt, cudaStream_t s);
+int splat3_f32(void* d_I, const void* go, const void* u, int64_t N, int64_t NI, int64_t C, const int64_t* sh,
+               double dt, cudaStream_t s);
+}  // namespace lgm
+
 using namespace lgm;
 
 #define DISPATCH_RD(dtype, dim, FN, ...)                                 \
@@ -300,6 +307,10 @@ extern "C" int lgm_interp_fwd(int dtype, void* out, const void* I, const void* u
   LGM_REQUIRE(shape_ok(dim, shape), "lgm_interp_fwd: Only two- and three-dimensional interpolation is supported");
   LGM_REQUIRE(N >= 0 && C >= 0 && NI >= 0 && N <= 65535, "lgm_interp_fwd: bad batch/channel count");
   LGM_REQUIRE(NI == N || (NI == 1 && N >= 1), "lgm_interp_fwd: image batch must equal the displacement batch or be 1");
+  if (dtype == LGM_F32 && dim == 3 && N > 0 && C > 0) {  // fp32 3-D fast path (gather3.cu)
+    int rc = interp3_f32(out, I, u, N, NI, C, shape, dt, (cudaStream_t)stream);
+    if (rc != LGM_EUNSUP) return rc;
+  }
   DISPATCH_RD(dtype, dim, interp_fwd_t, out, I, u, N, NI, C, shape, dt, (cudaStream_t)stream);
 }
 
@@ -309,6 +320,18 @@ extern "C" int lgm_interp_bwd(int dtype, void* d_I, void* d_u, const void* gout,
   LGM_REQUIRE(shape_ok(dim, shape), "lgm_interp_bwd: Only two- and three-dimensional interpolation is supported");
   LGM_REQUIRE(N >= 0 && C >= 0 && NI >= 0 && N <= 65535, "lgm_interp_bwd: bad batch/channel count");
   LGM_REQUIRE(NI == N || (NI == 1 && N >= 1), "lgm_interp_bwd: image batch must equal the displacement batch or be 1");
+  if (dtype == LGM_F32 && dim == 3 && d_I && N > 0 && C > 0) {
+    // fp32 3-D fast path for the splat (gather3.cu); d_u, if wanted, comes from the generic kernel
+    long long V = shape[0] * shape[1] * shape[2];
+    cudaError_t e = cudaMemsetAsync(d_I, 0, (size_t)(NI * C * V) * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error((int)e, "lgm_interp_bwd: memset: %s", cudaGetErrorString(e));
+    int rc = splat3_f32(d_I, gout, u, N, NI, C, shape, dt, (cudaStream_t)stream);
+    if (rc == LGM_OK) {
+      if (!d_u) return LGM_OK;
+      return interp_bwd_t<float, 3>(nullptr, d_u, gout, I, u, N, NI, C, shape, dt, (cudaStream_t)stream);
+    }
+    if (rc != LGM_EUNSUP) return rc;
+  }
   DISPATCH_RD(dtype, dim, interp_bwd_t, d_I, d_u, gout, I, u, N, NI, C, shape, dt, (cudaStream_t)stream);
 }
 
