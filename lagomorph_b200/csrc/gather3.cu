@@ -214,6 +214,73 @@ interp3_kernel(float* __restrict__ out, const float* __restrict__ I, const float
   }
 }
 
+// d_u of interp (cuda/interp.cu:224-233): d_u[d] = sum_c (gout_c * dt) * d/dx_d I_c(h), with the
+// corner-difference gradient of include/interp.h:315-326. Same mapping / gathers as interp3_kernel.
+template <int NV, bool UNIT_DT>
+__global__ void __launch_bounds__(256)
+interp_du3_kernel(float* __restrict__ d_u, const float* __restrict__ go, const float* __restrict__ I,
+                  const float* __restrict__ u, int X, int Y, int Z, int C, size_t I_batch_stride, float dh,
+                  float dl, double dt) {
+  const int j = blockIdx.y * 8 + threadIdx.y;
+  if (j >= Y) return;
+  const int i = blockIdx.z % X;
+  const int n = blockIdx.z / X;
+  const int sy = Z, sx = Y * Z;
+  const int V = X * sx;
+  const float* un = u + (size_t)n * 3 * V;
+  const float* gn = go + (size_t)n * C * V;
+  const float* In = I + (size_t)n * I_batch_stride;
+  float* dn = d_u + (size_t)n * 3 * V;
+  asm volatile("" : "+l"(In));
+  const int row = i * sx + j * sy;
+  const float fi = (float)i, fj = (float)j;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int k = (blockIdx.x * NV + v) * 32 + threadIdx.x;
+    if (k >= Z) break;
+    const int c0 = row + k;
+    const float A0 = __ldg(un + c0), A1 = __ldg(un + c0 + V), A2 = __ldg(un + c0 + 2 * V);
+    float hx, hy, hz;
+    const float fk = (float)k;
+    if (UNIT_DT) {
+      hx = __fadd_rn(fi, A0);
+      hy = __fadd_rn(fj, A1);
+      hz = __fadd_rn(fk, A2);
+    } else {
+      hx = coord_f32(fi, A0, dh, dl);
+      hy = coord_f32(fj, A1, dh, dl);
+      hz = coord_f32(fk, A2, dh, dl);
+    }
+    const Ax3 ax = axis_fast(hx, X), ay = axis_fast(hy, Y), az = axis_fast(hz, Z);
+    // the gradient needs the true (possibly coincident) corner values, so use the clamped pair
+    const unsigned rx0 = ax.i0 * sx, rx1 = ax.i1 * sx;
+    const unsigned ry0 = ay.i0 * sy, ry1 = ay.i1 * sy;
+    const unsigned i00 = rx0 + ry0 + az.i0, i01 = rx0 + ry1 + az.i0, i10 = rx1 + ry0 + az.i0, i11 = rx1 + ry1 + az.i0;
+    const int dz = az.i1 - az.i0;
+    const float t = ax.t, uu = ay.t, w = az.t;
+    const float omt = 1.f - t, omu = 1.f - uu, omv = 1.f - w;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    const float* Ic = In;
+    for (int c = 0; c < C; ++c, Ic += V) {
+      const float g = __ldg(gn + (size_t)c * V + c0);
+      const float gd = (float)((double)g * dt);  // "diff *= dt" in double, cuda/interp.cu:230
+      const float v0 = __ldg(Ic + i00), v4 = __ldg(Ic + i00 + dz);
+      const float v3 = __ldg(Ic + i01), v7 = __ldg(Ic + i01 + dz);
+      const float v1 = __ldg(Ic + i10), v5 = __ldg(Ic + i10 + dz);
+      const float v2 = __ldg(Ic + i11), v6 = __ldg(Ic + i11 + dz);
+      const float gx = omv * (omu * (v1 - v0) + uu * (v2 - v3)) + w * (omu * (v5 - v4) + uu * (v6 - v7));
+      const float gy = omv * (omt * (v3 - v0) + t * (v2 - v1)) + w * (omt * (v7 - v4) + t * (v6 - v5));
+      const float gz = omu * (omt * (v4 - v0) + t * (v5 - v1)) + uu * (omt * (v7 - v3) + t * (v6 - v2));
+      a0 = a0 + gx * gd;
+      a1 = a1 + gy * gd;
+      a2 = a2 + gz * gd;
+    }
+    dn[c0] = a0;
+    dn[c0 + V] = a1;
+    dn[c0 + 2 * V] = a2;
+  }
+}
+
 // Adjoint of interp (splat, cuda/interp.cu:185-244 d_I part): every voxel adds w_corner * gout to
 // its 8 corner voxels. Lanes are consecutive in z, so for smooth flows the upper-z corner of lane L
 // is the lower-z corner of lane L+1: those two contributions are merged with one warp shuffle and
@@ -351,6 +418,23 @@ int splat3_f32(void* d_I, const void* go, const void* u, int64_t N, int64_t NI, 
                                                    (int)sh[1], (int)sh[2], (int)C, ibs, dh, dl);
   }
   count_launch("interp_splat", s);
+  return finish(s, "lgm_interp_bwd");
+}
+
+int interp_du3_f32(void* d_u, const void* go, const void* I, const void* u, int64_t N, int64_t NI, int64_t C,
+                   const int64_t* sh, double dt, cudaStream_t s) {
+  if (!fast3_ok(d_u, go, u, N, sh) || C < 1 || C > 0x7fffffff / (sh[0] * sh[1] * sh[2])) return LGM_EUNSUP;
+  const size_t ibs = (NI < N) ? 0 : (size_t)C * sh[0] * sh[1] * sh[2];
+  dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * sh[0])), block(32, 8);
+  if (dt == 1.0) {
+    interp_du3_kernel<4, true><<<grid, block, 0, s>>>((float*)d_u, (const float*)go, (const float*)I, (const float*)u,
+                                                      (int)sh[0], (int)sh[1], (int)sh[2], (int)C, ibs, 1.f, 0.f, dt);
+  } else {
+    const float dh = (float)dt, dl = (float)(dt - (double)dh);
+    interp_du3_kernel<4, false><<<grid, block, 0, s>>>((float*)d_u, (const float*)go, (const float*)I, (const float*)u,
+                                                       (int)sh[0], (int)sh[1], (int)sh[2], (int)C, ibs, dh, dl, dt);
+  }
+  count_launch("interp_du", s);
   return finish(s, "lgm_interp_bwd");
 }
 

@@ -277,6 +277,8 @@ int interp3_f32(void* out, const void* I, const void* u, int64_t N, int64_t NI, 
                 double dt, cudaStream_t s);
 int splat3_f32(void* d_I, const void* go, const void* u, int64_t N, int64_t NI, int64_t C, const int64_t* sh,
                double dt, cudaStream_t s);
+int interp_du3_f32(void* d_u, const void* go, const void* I, const void* u, int64_t N, int64_t NI, int64_t C,
+                   const int64_t* sh, double dt, cudaStream_t s);
 }  // namespace lgm
 
 using namespace lgm;
@@ -320,17 +322,26 @@ extern "C" int lgm_interp_bwd(int dtype, void* d_I, void* d_u, const void* gout,
   LGM_REQUIRE(shape_ok(dim, shape), "lgm_interp_bwd: Only two- and three-dimensional interpolation is supported");
   LGM_REQUIRE(N >= 0 && C >= 0 && NI >= 0 && N <= 65535, "lgm_interp_bwd: bad batch/channel count");
   LGM_REQUIRE(NI == N || (NI == 1 && N >= 1), "lgm_interp_bwd: image batch must equal the displacement batch or be 1");
-  if (dtype == LGM_F32 && dim == 3 && d_I && N > 0 && C > 0) {
-    // fp32 3-D fast path for the splat (gather3.cu); d_u, if wanted, comes from the generic kernel
-    long long V = shape[0] * shape[1] * shape[2];
-    cudaError_t e = cudaMemsetAsync(d_I, 0, (size_t)(NI * C * V) * sizeof(float), (cudaStream_t)stream);
-    if (e != cudaSuccess) return set_error((int)e, "lgm_interp_bwd: memset: %s", cudaGetErrorString(e));
-    int rc = splat3_f32(d_I, gout, u, N, NI, C, shape, dt, (cudaStream_t)stream);
-    if (rc == LGM_OK) {
-      if (!d_u) return LGM_OK;
-      return interp_bwd_t<float, 3>(nullptr, d_u, gout, I, u, N, NI, C, shape, dt, (cudaStream_t)stream);
+  if (dtype == LGM_F32 && dim == 3 && N > 0 && C > 0) {
+    // fp32 3-D fast paths (gather3.cu): warp-aggregated splat for d_I, gather kernel for d_u;
+    // whatever they decline falls through to the generic kernel
+    cudaStream_t s = (cudaStream_t)stream;
+    bool done_I = (d_I == nullptr), done_u = (d_u == nullptr);
+    if (d_I) {
+      long long V = shape[0] * shape[1] * shape[2];
+      cudaError_t e = cudaMemsetAsync(d_I, 0, (size_t)(NI * C * V) * sizeof(float), s);
+      if (e != cudaSuccess) return set_error((int)e, "lgm_interp_bwd: memset: %s", cudaGetErrorString(e));
+      int rc = splat3_f32(d_I, gout, u, N, NI, C, shape, dt, s);
+      if (rc == LGM_OK) done_I = true;
+      else if (rc != LGM_EUNSUP) return rc;
     }
-    if (rc != LGM_EUNSUP) return rc;
+    if (d_u) {
+      int rc = interp_du3_f32(d_u, gout, I, u, N, NI, C, shape, dt, s);
+      if (rc == LGM_OK) done_u = true;
+      else if (rc != LGM_EUNSUP) return rc;
+    }
+    if (done_I && done_u) return LGM_OK;
+    return interp_bwd_t<float, 3>(done_I ? nullptr : d_I, done_u ? nullptr : d_u, gout, I, u, N, NI, C, shape, dt, s);
   }
   DISPATCH_RD(dtype, dim, interp_bwd_t, d_I, d_u, gout, I, u, N, NI, C, shape, dt, (cudaStream_t)stream);
 }
