@@ -112,6 +112,19 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
   const float fi = (float)i, fj = (float)j;
   const int xm = (i > 0) ? -sx : 0, xp = (i < X - 1) ? sx : 0;
   const int ym = (j > 0) ? -sy : 0, yp = (j < Y - 1) ? sy : 0;
+  // the centre loads of ALL chunks are issued up front: they gate everything else of a chunk, and
+  // 3*NV registers buy one full memory round trip of overlap per chunk
+  float Apre[NV][3];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int k = (blockIdx.x * NV + v) * 32 + threadIdx.x;
+    if (k < Z) {
+      const float* a0 = an + (row + k);
+      Apre[v][0] = __ldg(a0);
+      Apre[v][1] = __ldg(a0 + V);
+      Apre[v][2] = __ldg(a0 + 2 * V);
+    }
+  }
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int k = (blockIdx.x * NV + v) * 32 + threadIdx.x;
@@ -120,7 +133,7 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
     const float* a0 = an + c0;
     const float* a1 = a0 + V;
     const float* a2 = a1 + V;
-    const float A0 = __ldg(a0), A1 = __ldg(a1), A2 = __ldg(a2);
+    const float A0 = Apre[v][0], A1 = Apre[v][1], A2 = Apre[v][2];
     float hx, hy, hz;
     const float fk = (float)k;
     if (MODE == 0) {  // dt == 1: the double sum is exact before rounding
