@@ -259,7 +259,10 @@ static int get_plan(int dim, const int64_t* shape, cudaStream_t s, const FluidPl
 // ------------------------------------------------------------------------------------------
 // Fast path kernels
 // ------------------------------------------------------------------------------------------
-constexpr int kFftThreads = 256;
+#ifndef LGM_FFT_THREADS
+#define LGM_FFT_THREADS 256
+#endif
+constexpr int kFftThreads = LGM_FFT_THREADS;
 #ifndef LGM_XPASS_MINBLOCKS
 #define LGM_XPASS_MINBLOCKS 4  /* 64 registers: measured 0.254 -> 0.240 ms per C2 X pass vs 80 registers */
 #endif
