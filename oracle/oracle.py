@@ -281,3 +281,20 @@ def regrid(I, shape, origin=None, spacing=None, displacement=False):  # affine.p
     if displacement:
         reg = reg * (1.0 / torch.tensor(spacing, dtype=reg.dtype).view(1, d, *[1] * d))
     return reg
+
+
+# dagger / sym compositions, adjrep.py:104-145
+def ad_dagger(x, y, metric):
+    return metric.sharp(ad_star(x, metric.flat(y)))
+
+
+def Ad_dagger(phi, y, metric):
+    return metric.sharp(Ad_star(phi, metric.flat(y)))
+
+
+def sym(x, y, metric):
+    return -(ad_dagger(x, y, metric) + ad_dagger(y, x, metric))
+
+
+def sym_dagger(x, y, metric):
+    return ad_dagger(y, x, metric) - ad(x, y)

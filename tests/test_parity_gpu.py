@@ -243,3 +243,38 @@ def test_expmap_host_pipeline(lm, orc):
     out = lm.expmap_host(gm, m0, num_steps=3, chunk=2)
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("dim,sh", [(2, (16, 16)), (3, (8, 16, 16))])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dagger_sym_and_compose_variants(lm, orc, dim, sh, dtype):
+    """adjrep.py:104-145 compositions and the compose_* wrappers (deform.py:58-70)"""
+    params = [0.5, 0.0, 0.5]
+    om, gm = orc.FluidMetric(params), lm.FluidMetric(params)
+    x = randn((2, dim) + sh, dtype, 201)
+    y = randn((2, dim) + sh, dtype, 202)
+    phi = randn((2, dim) + sh, dtype, 203, 0.5)
+    tol = 5e-5 if dtype == torch.float32 else 1e-10
+    xc, yc, pc = x.cuda(), y.cuda(), phi.cuda()
+    assert relerr(lm.ad_dagger(xc, yc, gm), orc.ad_dagger(x, y, om)) <= tol
+    assert relerr(lm.Ad_dagger(pc, yc, gm), orc.Ad_dagger(phi, y, om)) <= tol
+    assert relerr(lm.sym(xc, yc, gm), orc.sym(x, y, om)) <= tol
+    assert relerr(lm.sym_dagger(xc, yc, gm), orc.sym_dagger(x, y, om)) <= tol
+    assert relerr(lm.compose_disp_vel(pc, xc, dt=-0.2), orc.compose_disp_vel(phi, x, dt=-0.2)) <= tol_for(dtype)
+    assert relerr(lm.compose_vel_disp(xc, pc, dt=0.3), orc.compose_vel_disp(x, phi, dt=0.3)) <= tol_for(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_expmap_mommask(lm, orc, dtype):
+    params = [0.1, 0.0, 0.01]
+    om, gm = orc.FluidMetric(params), lm.FluidMetric(params)
+    sh = (16, 16, 16)
+    m0 = smooth_field((2, 3) + sh, torch.float64, 73, amp=1.0, sigma=2.0)
+    m0 = (m0 * (2.0 / om.sharp(m0).abs().max())).to(dtype)
+    mask = (randn((2, 3) + sh, dtype, 74) > 0).to(dtype)
+    ref = orc.expmap(om, m0, num_steps=3, mommask=mask)
+    tol = 1e-4 if dtype == torch.float32 else 1e-10
+    assert relerr(lm.expmap(gm, m0.cuda(), num_steps=3, mommask=mask.cuda()), ref) <= tol          # fused path
+    bm = mask[:, :1]                                                                                # broadcast mask
+    ref = orc.expmap(om, m0, num_steps=3, mommask=bm)
+    assert relerr(lm.expmap(gm, m0.cuda(), num_steps=3, mommask=bm.cuda()), ref) <= tol            # unfused path
