@@ -162,22 +162,41 @@ def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chu
         out = torch.empty_like(m0_host, pin_memory=True)
     if N == 0:
         return out
-    chunk = max(1, min(int(chunk), N))
+    # chunk: an int (uniform chunks) or a list of chunk sizes. With an int the first and last chunks
+    # are halved (down to 1 subject) because their copy cannot hide behind any compute.
+    if isinstance(chunk, (list, tuple)):
+        sizes = [int(c) for c in chunk if int(c) > 0]
+        assert sum(sizes) == N, "chunk sizes must add up to the batch"
+    else:
+        chunk = max(1, min(int(chunk), N))
+        edge = max(1, chunk // 2)
+        sizes = []
+        left = N
+        if N > 2 * edge:
+            sizes.append(edge)
+            left -= 2 * edge
+            while left > 0:
+                sizes.append(min(chunk, left))
+                left -= sizes[-1]
+            sizes.append(edge)
+        else:
+            while left > 0:
+                sizes.append(min(chunk, left))
+                left -= sizes[-1]
+    maxc = max(sizes)
     cur = torch.cuda.current_stream(dev)
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     s_in.wait_stream(cur)
     s_out.wait_stream(cur)
     nbuf = 3
-    dbuf = [torch.empty((chunk,) + tuple(m0_host.shape[1:]), dtype=m0_host.dtype, device=dev) for _ in range(nbuf)]
+    dbuf = [torch.empty((maxc,) + tuple(m0_host.shape[1:]), dtype=m0_host.dtype, device=dev) for _ in range(nbuf)]
     in_done = [torch.cuda.Event() for _ in range(nbuf)]
-    out_done = [None] * nbuf   # result buffer of slot b has been copied out
     comp_done = [None] * nbuf  # input buffer of slot b has been consumed
-    results = []
-    starts = list(range(0, N, chunk))
+    starts = [sum(sizes[:i]) for i in range(len(sizes))]
 
     def issue_h2d(ci):
         b = ci % nbuf
-        n = min(chunk, N - starts[ci])
+        n = sizes[ci]
         with torch.cuda.stream(s_in):
             if comp_done[b] is not None:
                 s_in.wait_event(comp_done[b])
@@ -187,7 +206,7 @@ def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chu
     issue_h2d(0)
     for ci, st in enumerate(starts):
         b = ci % nbuf
-        n = min(chunk, N - st)
+        n = sizes[ci]
         if ci + 1 < len(starts):
             issue_h2d(ci + 1)
         cur.wait_event(in_done[b])
