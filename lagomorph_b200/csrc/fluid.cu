@@ -354,6 +354,7 @@ zinv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec, lon
   const long long row0 = (long long)blockIdx.x * L;
   for (int j = tid; j < Z; j += kFftThreads) tw[j] = tw_g[j];
   for (int j = tid; j < M; j += kFftThreads) twM[j] = tw_g[2 * j];
+#pragma unroll kSlabIoUnroll
   for (int idx = tid; idx < L * (M + 1); idx += kFftThreads) {
     const int l = idx / (M + 1), p = idx % (M + 1);
     C v;
