@@ -303,6 +303,25 @@ struct ColFFT {
     }
     fft_stage<R, N, BLOCK, RAD, L, true>(tile, rs, ls, tw, tid, nth);
   }
+  // all stages except the innermost one (which real_edge_stage() fuses with the real split)
+  static __device__ __forceinline__ void fwd_nolast(C* tile, int rs, int ls, const C* tw, int tid, int nth) {
+    if constexpr (!LASTSTAGE) {
+      fft_stage<R, N, BLOCK, RAD, L, false>(tile, rs, ls, tw, tid, nth);
+      if constexpr (!ColFFT<R, N, BLOCK / RAD, SI + 1, L>::LASTSTAGE) {
+        __syncthreads();
+        ColFFT<R, N, BLOCK / RAD, SI + 1, L>::fwd_nolast(tile, rs, ls, tw, tid, nth);
+      }
+    }
+  }
+  static __device__ __forceinline__ void inv_nolast(C* tile, int rs, int ls, const C* tw, int tid, int nth) {
+    if constexpr (!LASTSTAGE) {
+      if constexpr (!ColFFT<R, N, BLOCK / RAD, SI + 1, L>::LASTSTAGE) {
+        ColFFT<R, N, BLOCK / RAD, SI + 1, L>::inv_nolast(tile, rs, ls, tw, tid, nth);
+        __syncthreads();
+      }
+      fft_stage<R, N, BLOCK, RAD, L, true>(tile, rs, ls, tw, tid, nth);
+    }
+  }
   // variants whose first executed stage reads global memory (GIN) and/or whose last executed
   // stage writes global memory (GOUT); gin / gout describe those arrays.
   template <bool GIN, bool GOUT>
@@ -378,6 +397,191 @@ __device__ __forceinline__ void col_fft_fwd_from_global(typename Cx<R>::T* g, lo
   if constexpr (N / RAD > 1) {
     __syncthreads();
     ColFFT<R, N, N / RAD, 1, L>::fwd(tile, rs, ls, tw, tid, nth);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Real transform of 2M points through a complex FFT of M points on (x[2j], x[2j+1]) pairs, with the
+// split / unsplit folded into the LAST forward / FIRST inverse radix stage.
+//
+// In the last forward stage a block b (RAD consecutive rows) holds the frequencies
+// k = klow(b) + NB*k2, k2 < RAD, NB = M/RAD. The split pairs k with M-k, whose block has
+// klow' = (NB - klow) mod NB and k2' = RAD-1-k2 (k2' = RAD-k2 when klow == 0). A work item therefore
+// transforms the two partner blocks together and has every (k, M-k) pair in registers:
+//   X[k]   = 1/2[(Zk + conj Zm) - i W^k (Zk - conj Zm)],  Zm = Z[M-k], W = e^{-2 pi i / 2M}
+// so the separate split pass (one more shared-memory round trip plus a barrier) disappears.
+// The tile needs M+1 rows: row M receives the Nyquist word X[M].
+template <int N>
+__host__ __device__ __forceinline__ int fft_freq(int pos) {  // inverse of fft_pos
+  constexpr int b = ilog2(N);
+  constexpr int ns = (b + 3) / 4;
+  int k = 0, mult = 1, size = N;
+#pragma unroll
+  for (int s = 0; s < ns; ++s) {
+    const int r = 1 << stage_bits(b, s);
+    size /= r;
+    const int d = pos / size;
+    pos -= d * size;
+    k += d * mult;
+    mult *= r;
+  }
+  return k;
+}
+
+template <typename C>
+__device__ __forceinline__ void split_pair(C a, C b, C w, C& xk, C& xm) {
+  using R = decltype(a.x);
+  C s, d, t, w2, d2, t2;
+  s.x = a.x + b.x; s.y = a.y - b.y;
+  d.x = a.x - b.x; d.y = a.y + b.y;
+  t = cmul(w, d);
+  xk.x = R(0.5) * (s.x + t.y);
+  xk.y = R(0.5) * (s.y - t.x);
+  w2.x = -w.x; w2.y = w.y;
+  d2.x = -d.x; d2.y = d.y;
+  t2 = cmul(w2, d2);
+  xm.x = R(0.5) * (s.x + t2.y);
+  xm.y = R(0.5) * (-s.y - t2.x);
+}
+template <typename C>
+__device__ __forceinline__ void unsplit_pair(C a, C b, C w, C& zk, C& zm) {
+  C s, d, t, d2, t2;
+  s.x = a.x + b.x; s.y = a.y - b.y;
+  d.x = a.x - b.x; d.y = a.y + b.y;
+  t = cmulc(d, w);
+  zk.x = s.x - t.y;
+  zk.y = s.y + t.x;
+  d2.x = -d.x; d2.y = d.y;
+  t2 = cmul(d2, w);
+  zm.x = s.x + t2.y;
+  zm.y = -s.y - t2.x;
+}
+
+// twz: table of 2M entries e^{-2 pi i j / 2M}. Rows of the tile: element (r, l) at tile[r*rs + l*ls].
+template <typename R, int M, int L, bool INV>
+__device__ __forceinline__ void real_edge_stage(typename Cx<R>::T* tile, int rs, int ls,
+                                                const typename Cx<R>::T* __restrict__ twz, int tid, int nth) {
+  using C = typename Cx<R>::T;
+  constexpr int bM = ilog2(M), ns = (bM + 3) / 4;
+  constexpr int RAD = 1 << stage_bits(bM, ns - 1);
+  constexpr int NB = M / RAD;
+  constexpr int NP = NB / 2 + 1;
+  constexpr int BITS = ilog2(RAD);
+  for (int it = tid; it < L * NP; it += nth) {
+    const int l = it % L, kl = it / L;
+    const int klp = (NB - kl) % NB;
+    const int b0 = fft_pos<NB>(kl), b1 = fft_pos<NB>(klp);
+    C* p0 = tile + (b0 * RAD) * rs + l * ls;
+    C* p1 = tile + (b1 * RAD) * rs + l * ls;
+    C x[RAD], y[RAD];
+    if (!INV) {
+#pragma unroll
+      for (int n = 0; n < RAD; ++n) x[n] = p0[n * rs];
+      reg_fft<RAD, false>(x);  // x[bitrev(k2)] = Z[kl + NB*k2]
+      if (kl == 0) {
+        C a = x[0], x0, xM;
+        x0.x = a.x + a.y; x0.y = R(0);
+        xM.x = a.x - a.y; xM.y = R(0);
+        p0[0] = x0;
+        tile[M * rs + l * ls] = xM;
+#pragma unroll
+        for (int k2 = 1; k2 <= RAD / 2; ++k2) {
+          C xk, xm;
+          split_pair(x[bitrev(k2, BITS)], x[bitrev(RAD - k2, BITS)], twz[NB * k2], xk, xm);
+          p0[k2 * rs] = xk;
+          if (k2 != RAD - k2) p0[(RAD - k2) * rs] = xm;
+        }
+      } else if (klp == kl) {
+#pragma unroll
+        for (int k2 = 0; k2 < RAD / 2; ++k2) {
+          C xk, xm;
+          split_pair(x[bitrev(k2, BITS)], x[bitrev(RAD - 1 - k2, BITS)], twz[kl + NB * k2], xk, xm);
+          p0[k2 * rs] = xk;
+          p0[(RAD - 1 - k2) * rs] = xm;
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < RAD; ++n) y[n] = p1[n * rs];
+        reg_fft<RAD, false>(y);
+#pragma unroll
+        for (int k2 = 0; k2 < RAD; ++k2) {
+          C xk, xm;
+          split_pair(x[bitrev(k2, BITS)], y[bitrev(RAD - 1 - k2, BITS)], twz[kl + NB * k2], xk, xm);
+          p0[k2 * rs] = xk;
+          p1[(RAD - 1 - k2) * rs] = xm;
+        }
+      }
+    } else {
+      // unsplit Z'[k] = (Xk + conj Xm) + i conj(W^k)(Xk - conj Xm), then the inverse RAD-point stage
+      if (kl == 0) {
+        const R r0 = p0[0].x, rM = tile[M * rs + l * ls].x;  // imaginary parts of DC / Nyquist ignored (C2R)
+        x[0].x = r0 + rM;
+        x[0].y = r0 - rM;
+#pragma unroll
+        for (int k2 = 1; k2 <= RAD / 2; ++k2) {
+          C zk, zm;
+          unsplit_pair(p0[k2 * rs], p0[(RAD - k2) * rs], twz[NB * k2], zk, zm);
+          x[k2] = zk;
+          if (k2 != RAD - k2) x[RAD - k2] = zm;
+        }
+        reg_fft<RAD, true>(x);
+#pragma unroll
+        for (int i = 0; i < RAD; ++i) p0[bitrev(i, BITS) * rs] = x[i];
+      } else if (klp == kl) {
+#pragma unroll
+        for (int k2 = 0; k2 < RAD / 2; ++k2) {
+          C zk, zm;
+          unsplit_pair(p0[k2 * rs], p0[(RAD - 1 - k2) * rs], twz[kl + NB * k2], zk, zm);
+          x[k2] = zk;
+          x[RAD - 1 - k2] = zm;
+        }
+        reg_fft<RAD, true>(x);
+#pragma unroll
+        for (int i = 0; i < RAD; ++i) p0[bitrev(i, BITS) * rs] = x[i];
+      } else {
+#pragma unroll
+        for (int k2 = 0; k2 < RAD; ++k2) {
+          C zk, zm;
+          unsplit_pair(p0[k2 * rs], p1[(RAD - 1 - k2) * rs], twz[kl + NB * k2], zk, zm);
+          x[k2] = zk;
+          y[RAD - 1 - k2] = zm;
+        }
+        reg_fft<RAD, true>(x);
+        reg_fft<RAD, true>(y);
+#pragma unroll
+        for (int i = 0; i < RAD; ++i) {
+          p0[bitrev(i, BITS) * rs] = x[i];
+          p1[bitrev(i, BITS) * rs] = y[i];
+        }
+      }
+    }
+  }
+}
+
+// real forward: tile rows 0..M-1 hold z[j] = (x[2j], x[2j+1]); on return rows 0..M hold the half
+// spectrum in storage order (row M = Nyquist). twM: e^{-2 pi i j / M} (M entries).
+template <typename R, int M, int L>
+__device__ __forceinline__ void real_fft_fwd(typename Cx<R>::T* tile, int rs, int ls,
+                                             const typename Cx<R>::T* twM, const typename Cx<R>::T* twz,
+                                             int tid, int nth) {
+  constexpr int ns = (ilog2(M) + 3) / 4;
+  if constexpr (ns > 1) {
+    ColFFT<R, M, M, 0, L>::fwd_nolast(tile, rs, ls, twM, tid, nth);
+    __syncthreads();
+  }
+  real_edge_stage<R, M, L, false>(tile, rs, ls, twz, tid, nth);
+}
+// real inverse: rows 0..M hold the half spectrum; on return rows 0..M-1 hold the (unnormalised)
+// time samples as (x[2j], x[2j+1]) pairs.
+template <typename R, int M, int L>
+__device__ __forceinline__ void real_fft_inv(typename Cx<R>::T* tile, int rs, int ls,
+                                             const typename Cx<R>::T* twM, const typename Cx<R>::T* twz,
+                                             int tid, int nth) {
+  constexpr int ns = (ilog2(M) + 3) / 4;
+  real_edge_stage<R, M, L, true>(tile, rs, ls, twz, tid, nth);
+  if constexpr (ns > 1) {
+    __syncthreads();
+    ColFFT<R, M, M, 0, L>::inv_nolast(tile, rs, ls, twM, tid, nth);
   }
 }
 

@@ -300,38 +300,8 @@ zfwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in, long
   C* twM = tw + Z;  // M entries, compacted
   for (int j = tid; j < M; j += kFftThreads) twM[j] = tw[2 * j];
   __syncthreads();
-  col_fft_fwd<R, M, L>(tile, P, 1, twM, tid, kFftThreads);
-  __syncthreads();
-  // split: X[k] = 1/2[(Zk + conj Z(M-k)) - i W_Z^k (Zk - conj Z(M-k))]
-  for (int idx = tid; idx < L * (M / 2 + 1); idx += kFftThreads) {
-    const int l = idx % L, k = idx / L;
-    if (k == 0) {
-      C a = tile[l];  // fft_pos(0) == 0
-      C x0, xm;
-      x0.x = a.x + a.y; x0.y = R(0);
-      xm.x = a.x - a.y; xm.y = R(0);
-      tile[l] = x0;
-      tile[M * P + l] = xm;
-    } else {
-      const int pa = fft_pos<M>(k), pb = fft_pos<M>(M - k);
-      C a = tile[pa * P + l], b = tile[pb * P + l], w = tw[k];
-      C s, d, t, xk, xm;
-      s.x = a.x + b.x; s.y = a.y - b.y;
-      d.x = a.x - b.x; d.y = a.y + b.y;
-      t = cmul(w, d);
-      xk.x = R(0.5) * (s.x + t.y);
-      xk.y = R(0.5) * (s.y - t.x);
-      // partner: s' = conj(s), d' = (-d.x, d.y), w' = (-w.x, w.y)
-      C w2, d2, t2;
-      w2.x = -w.x; w2.y = w.y;
-      d2.x = -d.x; d2.y = d.y;
-      t2 = cmul(w2, d2);
-      xm.x = R(0.5) * (s.x + t2.y);
-      xm.y = R(0.5) * (-s.y - t2.x);
-      tile[pa * P + l] = xk;
-      if (pb != pa) tile[pb * P + l] = xm;
-    }
-  }
+  // half-length complex FFT with the real split fused into its last radix stage (fft.cuh)
+  real_fft_fwd<R, M, L>(tile, P, 1, twM, tw, tid, kFftThreads);
   __syncthreads();
   for (int idx = tid; idx < L * (M + 1); idx += kFftThreads) {
     const int l = idx / (M + 1), p = idx % (M + 1);
@@ -363,36 +333,8 @@ zinv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec, lon
     tile[p * P + l] = v;
   }
   __syncthreads();
-  // unsplit: Z'[k] = (Xk + conj X(M-k)) + i conj(W^k) (Xk - conj X(M-k))
-  for (int idx = tid; idx < L * (M / 2 + 1); idx += kFftThreads) {
-    const int l = idx % L, k = idx / L;
-    if (k == 0) {
-      R r0 = tile[l].x, rm = tile[M * P + l].x;  // imaginary parts of DC/Nyquist are ignored (C2R)
-      C z;
-      z.x = r0 + rm;
-      z.y = r0 - rm;
-      tile[l] = z;
-    } else {
-      const int pa = fft_pos<M>(k), pb = fft_pos<M>(M - k);
-      C a = tile[pa * P + l], b = tile[pb * P + l], w = tw[k];
-      C s, d, t, zk, zm;
-      s.x = a.x + b.x; s.y = a.y - b.y;   // Xk + conj Xm
-      d.x = a.x - b.x; d.y = a.y + b.y;   // Xk - conj Xm
-      t = cmulc(d, w);                    // conj(w) * d
-      zk.x = s.x - t.y;                   // + i*t
-      zk.y = s.y + t.x;
-      // partner: s' = conj(s), d' = (-d.x, d.y), factor i * (-w)
-      C d2, t2;
-      d2.x = -d.x; d2.y = d.y;
-      t2 = cmul(d2, w);
-      zm.x = s.x + t2.y;                  // - i*t2
-      zm.y = -s.y - t2.x;
-      tile[pa * P + l] = zk;
-      if (pb != pa) tile[pb * P + l] = zm;
-    }
-  }
-  __syncthreads();
-  col_fft_inv<R, M, L>(tile, P, 1, twM, tid, kFftThreads);
+  // unsplit fused into the first radix stage of the inverse half-length FFT (fft.cuh)
+  real_fft_inv<R, M, L>(tile, P, 1, twM, tw, tid, kFftThreads);
   __syncthreads();
   C* out2 = reinterpret_cast<C*>(out);
   for (int idx = tid; idx < L * M; idx += kFftThreads) {
@@ -428,35 +370,7 @@ slab_fwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in,
     tile[j * P + y] = in2[idx];
   }
   __syncthreads();
-  col_fft_fwd<R, M, Y>(tile, P, 1, twM, tid, kFftThreads);
-  __syncthreads();
-  for (int idx = tid; idx < Y * (M / 2 + 1); idx += kFftThreads) {
-    const int l = idx % Y, k = idx / Y;
-    if (k == 0) {
-      C a = tile[l];
-      C x0, xm;
-      x0.x = a.x + a.y; x0.y = R(0);
-      xm.x = a.x - a.y; xm.y = R(0);
-      tile[l] = x0;
-      tile[M * P + l] = xm;
-    } else {
-      const int pa = fft_pos<M>(k), pb = fft_pos<M>(M - k);
-      C a = tile[pa * P + l], b = tile[pb * P + l], w = twz[k];
-      C s, d, t, xk, xm, w2, d2, t2;
-      s.x = a.x + b.x; s.y = a.y - b.y;
-      d.x = a.x - b.x; d.y = a.y + b.y;
-      t = cmul(w, d);
-      xk.x = R(0.5) * (s.x + t.y);
-      xk.y = R(0.5) * (s.y - t.x);
-      w2.x = -w.x; w2.y = w.y;
-      d2.x = -d.x; d2.y = d.y;
-      t2 = cmul(w2, d2);
-      xm.x = R(0.5) * (s.x + t2.y);
-      xm.y = R(0.5) * (-s.y - t2.x);
-      tile[pa * P + l] = xk;
-      if (pb != pa) tile[pb * P + l] = xm;
-    }
-  }
+  real_fft_fwd<R, M, Y>(tile, P, 1, twM, twz, tid, kFftThreads);  // Z: half-length FFT + fused split
   __syncthreads();
   // Y transform; its last stage stores straight to the spectrum slab [ry][rz] (lanes over rz)
   GSide<C> gout{spec + (size_t)blockIdx.x * Y * ZC, ZC, ZC};
@@ -484,33 +398,7 @@ slab_inv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec,
   GSide<C> gin{const_cast<C*>(spec) + (size_t)blockIdx.x * Y * ZC, ZC, ZC};
   ColFFT<R, Y, Y, 0, ZC>::template inv_g<true, false>(tile, 1, P, twy, tid, kFftThreads, gin, gin);
   __syncthreads();
-  for (int idx = tid; idx < Y * (M / 2 + 1); idx += kFftThreads) {
-    const int l = idx % Y, k = idx / Y;
-    if (k == 0) {
-      R r0 = tile[l].x, rm = tile[M * P + l].x;
-      C z;
-      z.x = r0 + rm;
-      z.y = r0 - rm;
-      tile[l] = z;
-    } else {
-      const int pa = fft_pos<M>(k), pb = fft_pos<M>(M - k);
-      C a = tile[pa * P + l], b = tile[pb * P + l], w = twz[k];
-      C s, d, t, zk, zm, d2, t2;
-      s.x = a.x + b.x; s.y = a.y - b.y;
-      d.x = a.x - b.x; d.y = a.y + b.y;
-      t = cmulc(d, w);
-      zk.x = s.x - t.y;
-      zk.y = s.y + t.x;
-      d2.x = -d.x; d2.y = d.y;
-      t2 = cmul(d2, w);
-      zm.x = s.x + t2.y;
-      zm.y = -s.y - t2.x;
-      tile[pa * P + l] = zk;
-      if (pb != pa) tile[pb * P + l] = zm;
-    }
-  }
-  __syncthreads();
-  col_fft_inv<R, M, Y>(tile, P, 1, twM, tid, kFftThreads);
+  real_fft_inv<R, M, Y>(tile, P, 1, twM, twz, tid, kFftThreads);  // fused unsplit + inverse half-length FFT
   __syncthreads();
   C* o2 = reinterpret_cast<C*>(out) + (size_t)blockIdx.x * Y * M;
 #pragma unroll 4
