@@ -148,6 +148,20 @@ int lgm_epdiff_step_fwd(int dtype, void* phiinv_out, const void* phiinv, const v
                         const void* mommask, int64_t N, int dim, const int64_t* shape, double dt,
                         double alpha, double beta, double gamma, void* scratch,
                         int64_t scratch_bytes, void* stream);
+/* Backward of one EPDiff step: what autograd does for lddmm.py:39-44 through
+ * InterpFunction.backward (deform.py:31-41), JacobianTimesVectorFieldFunction.backward
+ * (diff.py:29-35) and FluidMetricOperator.backward (metric.py:21-34), as three fused kernels
+ * around one sharp. fp32, 3-D, shape[2] % 32 == 0 only: lgm_epdiff_bwd_scratch_bytes returns -1
+ * (and the step LGM_EUNSUP) otherwise; callers then chain lgm_interp_bwd / lgm_jtvf_bwd.
+ *   g_phi     in: dL/dphiinv_out; out (need_phi): dL/dphiinv. Updated in place.
+ *   d_m0      accumulator (need_m0): dL/dm0 of this step is ADDED; zero it before the first step.
+ *   splat_acc (N,3,...) accumulator used when need_phi: all zeros on entry, all zeros again on return.
+ *   phiinv, v the step's input displacement and its velocity v = sharp(Ad_star(phiinv, m0)*mommask). */
+int64_t lgm_epdiff_bwd_scratch_bytes(int dtype, int64_t N, int dim, const int64_t* shape);
+int lgm_epdiff_step_bwd(int dtype, void* g_phi, void* d_m0, void* splat_acc, const void* phiinv,
+                        const void* v, const void* m0, const void* mommask, int64_t N, int dim,
+                        const int64_t* shape, double dt, double alpha, double beta, double gamma,
+                        void* scratch, int64_t scratch_bytes, int need_phi, int need_m0, void* stream);
 
 #ifdef __cplusplus
 }

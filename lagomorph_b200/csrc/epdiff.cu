@@ -82,3 +82,58 @@ extern "C" int lgm_epdiff_step_fwd(int dtype, void* phiinv_out, const void* phii
   }
   return LGM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Backward of one step (fp32 3-D; see epdiff_bwd.cu for the kernels).
+// ------------------------------------------------------------------------------------------------
+namespace lgm {
+bool epdiff_bwd3_ok(int64_t N, const int64_t* sh);
+int compose_bwd3_f32(void* dv, void* S, const void* G, const void* phi, const void* v, int64_t N,
+                     const int64_t* sh, double ds, bool need_phi, cudaStream_t s);
+int adstar_bwd3_f32(void* mi, void* d_m0, void* S, const void* phi, const void* dm, const void* m0, int64_t N,
+                    const int64_t* sh, bool need_m0, bool need_phi, cudaStream_t s);
+int stencil_bwd3_f32(void* G, void* S, const void* mi, const void* dm, int64_t N, const int64_t* sh,
+                     cudaStream_t s);
+}  // namespace lgm
+
+extern "C" int64_t lgm_epdiff_bwd_scratch_bytes(int dtype, int64_t N, int dim, const int64_t* shape) {
+  if (dtype != LGM_F32 || dim != 3 || N < 1 || !epdiff_bwd3_ok(N, shape)) return -1;
+  const size_t field = align_up((size_t)(N * 3 * shape[0] * shape[1] * shape[2]) * 4, 256);
+  return (int64_t)(2 * field + (size_t)lgm_fluid_workspace_bytes(dtype, N, dim, shape));
+}
+
+extern "C" int lgm_epdiff_step_bwd(int dtype, void* g_phi, void* d_m0, void* splat_acc, const void* phiinv,
+                                   const void* v, const void* m0, const void* mommask, int64_t N, int dim,
+                                   const int64_t* shape, double dt, double alpha, double beta, double gamma,
+                                   void* scratch, int64_t scratch_bytes, int need_phi, int need_m0,
+                                   void* stream) {
+  const int64_t need = lgm_epdiff_bwd_scratch_bytes(dtype, N, dim, shape);
+  if (need < 0) return set_error(LGM_EUNSUP, "lgm_epdiff_step_bwd: only fp32 3-D volumes with Z %% 32 == 0");
+  if (scratch_bytes < need)
+    return set_error(LGM_ENOSPC, "lgm_epdiff_step_bwd: scratch too small (%lld < %lld bytes)",
+                     (long long)scratch_bytes, (long long)need);
+  LGM_REQUIRE(g_phi && phiinv && v && m0 && scratch, "lgm_epdiff_step_bwd: null pointer");
+  LGM_REQUIRE(!need_phi || splat_acc, "lgm_epdiff_step_bwd: splat_acc required when need_phi");
+  LGM_REQUIRE(!need_m0 || d_m0, "lgm_epdiff_step_bwd: d_m0 required when need_m0");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long V = shape[0] * shape[1] * shape[2];
+  const size_t field = align_up((size_t)(N * 3 * V) * 4, 256);
+  void* W = scratch;                        // d_v, then d_m in place
+  void* MI = (char*)scratch + field;        // m0(x + phiinv), for the stencil pass
+  void* ws = (char*)scratch + 2 * field;
+  // the gradient w.r.t. v is needed for both outputs (d_m0 and d_phiinv depend on d_m = sharp(d_v))
+  int rc = compose_bwd3_f32(W, splat_acc, g_phi, phiinv, v, N, shape, -dt, need_phi != 0, s);
+  if (rc) return rc;
+  rc = lgm_fluid_apply(dtype, W, W, N, dim, shape, 1, alpha, beta, gamma, ws, scratch_bytes - (int64_t)(2 * field), stream);
+  if (rc) return rc;
+  if (mommask) {
+    const long long total = N * 3 * V;
+    mul_mask_kernel<float><<<(unsigned)cdiv(total, 256), 256, 0, s>>>((float*)W, (const float*)mommask, total, total);
+    count_launch("mul_mask", s);
+  }
+  if (!need_phi && !need_m0) return LGM_OK;
+  rc = adstar_bwd3_f32(MI, d_m0, splat_acc, phiinv, W, m0, N, shape, need_m0 != 0, need_phi != 0, s);
+  if (rc) return rc;
+  if (need_phi) rc = stencil_bwd3_f32(g_phi, splat_acc, MI, W, N, shape, s);
+  return rc;
+}

@@ -1,0 +1,80 @@
+// gather_common.cuh -- coordinate / corner helpers shared by the fp32 3-D gather and splat kernels
+// (gather3.cu forward paths, epdiff_bwd.cu fused backward).
+#pragma once
+#include "common.cuh"
+
+namespace lgm {
+
+// RN_f32(fi + d*u) for d = dh + dl (double split in two floats), product and sum carried as
+// float pairs; equals the double-rounded reference value except on ~2^-21 of inputs (1 ulp).
+__device__ __forceinline__ float coord_f32(float fi, float u, float dh, float dl) {
+  float ph = __fmul_rn(dh, u);
+  float pe = __fmaf_rn(dh, u, -ph);
+  float pl = __fmaf_rn(dl, u, pe);
+  float sh = __fadd_rn(fi, ph);
+  float bb = __fsub_rn(sh, fi);
+  float se = __fadd_rn(__fsub_rn(fi, __fsub_rn(sh, bb)), __fsub_rn(ph, bb));
+  return __fadd_rn(sh, __fadd_rn(se, pl));
+}
+
+struct Ax3 {
+  int i0, i1;
+  float t;
+};
+
+// floor / fraction / clamped corner indices of one coordinate. Coordinates are first clamped to
+// +-2^22 voxels (far outside any volume: both corners are the border voxel there, and the result is
+// the border value for any weight), which lets floor() be a magic-number add with no slow path.
+__device__ __forceinline__ Ax3 axis_fast(float x, int n) {
+  Ax3 a;
+  x = fminf(fmaxf(x, -4194304.f), 4194304.f);
+  float r = __fadd_rn(x, 12582912.f);  // 1.5 * 2^23: rounds x to an integer in the mantissa
+  int f = __float_as_int(r) - 0x4B400000;
+  float rf = __fsub_rn(r, 12582912.f);
+  if (rf > x) {
+    rf -= 1.f;
+    f -= 1;
+  }
+  a.t = x - rf;
+  a.i0 = min(max(f, 0), n - 1);
+  a.i1 = min(max(f + 1, 0), n - 1);
+  return a;
+}
+
+// 8-corner gather + nested lerp (corner numbering / evaluation order of include/interp.h:91-122).
+// i00..i11 are the element indices of the four (x,y) corner rows at the lower z corner; the upper z
+// corner is always the +1 neighbour (an immediate offset on the same address register), see z_pair().
+__device__ __forceinline__ float trilerp(const float* __restrict__ img, unsigned i00, unsigned i01,
+                                         unsigned i10, unsigned i11, float t, float u, float v,
+                                         float omt, float omu, float omv) {
+  const float* p00 = img + i00;
+  const float* p01 = img + i01;
+  const float* p10 = img + i10;
+  const float* p11 = img + i11;
+  float v0 = __ldg(p00), v4 = __ldg(p00 + 1);
+  float v3 = __ldg(p01), v7 = __ldg(p01 + 1);
+  float v1 = __ldg(p10), v5 = __ldg(p10 + 1);
+  float v2 = __ldg(p11), v6 = __ldg(p11 + 1);
+  return omv * (omu * (omt * v0 + t * v1) + u * (omt * v3 + t * v2)) +
+         v * (omu * (omt * v4 + t * v5) + u * (omt * v7 + t * v6));
+}
+
+// Along the contiguous axis the two corners are fetched as (zs, zs+1) with zs <= Z-2 so that the
+// pair never leaves the row. Where the reference clamps both corners onto one border voxel
+// ((1-v)*B + v*B) the weight is replaced by 0 (lower border) or 1 (upper border): the same value
+// up to the rounding of (1-v)*B + v*B, i.e. <= 1 ulp, and only outside the volume.
+__device__ __forceinline__ void z_pair(const Ax3& az, int Z, int& zs, float& v) {
+  zs = min(az.i0, Z - 2);
+  v = az.t;
+  if (az.i1 == az.i0) v = (az.i0 == 0) ? 0.f : 1.f;
+}
+
+// RN_f32(g * d) for a double d = dh + dl: stands in for the reference's "(float)((double)g * dt)"
+// (cuda/interp.cu:230) without fp64 instructions; equal except for rare double-rounding ties (1 ulp).
+__device__ __forceinline__ float mul_f32_by_double(float g, float dh, float dl) {
+  float ph = __fmul_rn(g, dh);
+  float pe = __fmaf_rn(g, dh, -ph);
+  return __fadd_rn(ph, __fmaf_rn(g, dl, pe));
+}
+
+}  // namespace lgm

@@ -1,5 +1,6 @@
 """LDDMM vector-momentum geodesic shooting (mirror of lagomorph/lddmm.py:20-105)."""
 import math
+import os
 
 import torch
 
@@ -58,6 +59,94 @@ def _fusable(metric, m0, phiinv, mommask):
     return mommask is None or (mommask.shape == m0.shape and mommask.dtype == m0.dtype and mommask.is_cuda)
 
 
+def _fused_bwd_ok(metric, m0, phiinv, mommask):
+    """fp32 3-D CUDA fields with Z % 32 == 0: the step's backward runs as lgm_epdiff_step_bwd."""
+    if os.environ.get("LGM_FUSED_BWD", "1") == "0" or not isinstance(metric, FluidMetric):
+        return False
+    if not (m0.is_cuda and phiinv.is_cuda and m0.shape == phiinv.shape and m0.dtype == phiinv.dtype):
+        return False
+    if m0.dtype != torch.float32 or m0.dim() != 5 or m0.shape[1] != 3 or m0.shape[0] < 1:
+        return False
+    if mommask is not None and not (mommask.shape == m0.shape and mommask.dtype == m0.dtype and mommask.is_cuda):
+        return False
+    return int(L.lib.lgm_epdiff_bwd_scratch_bytes(L.dtype_code(m0), m0.shape[0], 3, L.shape_arr(m0.shape[2:]))) >= 0
+
+
+def _steps_saving(metric, m0, dt, N, phiinv, mommask):
+    """N forward steps keeping each step's input displacement and velocity (what the backward reads)."""
+    phis, vs = [], []
+    with torch.no_grad():
+        for n in range(N):
+            m = adjrep.Ad_star(phiinv, m0)
+            if mommask is not None:
+                m = m * mommask
+            v = metric.sharp(m)
+            phis.append(phiinv)
+            vs.append(v)
+            phiinv = deform.compose_disp_vel(phiinv, v, dt=-dt)
+    return phiinv, phis, vs
+
+
+def _steps_backward(metric, m0, dt, phis, vs, mommask, gradout, need_m0, need_phi):
+    """Backward of the steps recorded by _steps_saving, last step first: one lgm_epdiff_step_bwd per
+    step; dL/dm0 accumulates in place over the steps, dL/dphiinv is carried in `g`."""
+    dev = m0.device
+    code, N = L.dtype_code(m0), m0.shape[0]
+    sh = L.shape_arr(m0.shape[2:])
+    nbytes = int(L.lib.lgm_epdiff_bwd_scratch_bytes(code, N, 3, sh))
+    scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    g = gradout.contiguous().clone()
+    d_m0 = torch.zeros_like(m0) if need_m0 else None
+    acc = torch.zeros_like(m0) if (need_phi or len(phis) > 1) else None
+    alpha, beta, gamma = [float(p) for p in metric.params]
+    with torch.cuda.device(dev):
+        for k in reversed(range(len(phis))):
+            want_phi = need_phi or k > 0
+            if not (want_phi or need_m0):
+                break
+            L.check(L.lib.lgm_epdiff_step_bwd(code, L.ptr(g), L.ptr(d_m0), L.ptr(acc), L.ptr(phis[k]), L.ptr(vs[k]),
+                                              L.ptr(m0), L.ptr(mommask), N, 3, sh, float(dt), alpha, beta, gamma,
+                                              L.ptr(scratch), nbytes, int(want_phi), int(need_m0),
+                                              L.stream_ptr(dev)))
+    return d_m0, (g if need_phi else None)
+
+
+class EPDiffShootFunction(torch.autograd.Function):
+    """N EPDiff steps with a hand-written backward (fp32 3-D): forward keeps (phiinv_k, v_k) per step
+    -- or, with save=False, only the inputs and replays the block in backward (activation
+    checkpointing, the working form of lddmm.py:47-70)."""
+
+    @staticmethod
+    def forward(ctx, metric, m0, dt, N, phiinv, mommask, save):
+        m0c, pc = L.aligned(m0.detach()), L.aligned(phiinv.detach())
+        mk = None if mommask is None else mommask.detach().contiguous()
+        ctx.metric, ctx.dt, ctx.N, ctx.save, ctx.mk = metric, dt, N, save, mk
+        if save:
+            out, phis, vs = _steps_saving(metric, m0c, dt, N, pc, mk)
+            ctx.nsaved = len(phis)
+            ctx.save_for_backward(m0c, *phis, *vs)
+        else:
+            out = pc
+            with torch.no_grad():
+                for n in range(N):
+                    out = EPDiff_step(metric, m0c, dt, out, mommask=mk)
+            ctx.save_for_backward(m0c, pc)
+        return out
+
+    @staticmethod
+    def backward(ctx, gradout):
+        need_m0, need_phi = ctx.needs_input_grad[1], ctx.needs_input_grad[4]
+        if ctx.save:
+            m0c = ctx.saved_tensors[0]
+            phis = list(ctx.saved_tensors[1:1 + ctx.nsaved])
+            vs = list(ctx.saved_tensors[1 + ctx.nsaved:])
+        else:
+            m0c, pc = ctx.saved_tensors
+            _, phis, vs = _steps_saving(ctx.metric, m0c, ctx.dt, ctx.N, pc, ctx.mk)
+        d_m0, d_phi = _steps_backward(ctx.metric, m0c, ctx.dt, phis, vs, ctx.mk, gradout, need_m0, need_phi)
+        return None, d_m0, None, None, d_phi, None, None
+
+
 def EPDiff_step(metric, m0, dt, phiinv, mommask=None):
     """phiinv <- -dt*v + phiinv(x - dt*v), v = sharp(Ad_star(phiinv, m0)) (lddmm.py:39-44).
 
@@ -67,6 +156,8 @@ def EPDiff_step(metric, m0, dt, phiinv, mommask=None):
         m0c, pc = L.aligned(m0), L.aligned(phiinv)
         mk = None if mommask is None else mommask.contiguous()
         return _fused_step(metric, m0c, dt, pc, mk, _StepWorkspace(m0c), torch.empty_like(pc))
+    if _needs_grad(m0, phiinv) and not _needs_grad(mommask) and _fused_bwd_ok(metric, m0, phiinv, mommask):
+        return EPDiffShootFunction.apply(metric, m0, dt, 1, phiinv, mommask, True)
     m = adjrep.Ad_star(phiinv, m0)
     if mommask is not None:
         m = m * mommask
@@ -108,6 +199,8 @@ class EPDiffStepsFunction(torch.autograd.Function):
 
 
 def EPDiff_steps(metric, m0, dt, N, phiinv, mommask=None):
+    if not _needs_grad(mommask) and _fused_bwd_ok(metric, m0, phiinv, mommask):
+        return EPDiffShootFunction.apply(metric, m0, dt, N, phiinv, mommask, False)
     return EPDiffStepsFunction.apply(metric, m0, dt, N, phiinv, mommask)
 
 
@@ -129,6 +222,9 @@ def expmap(metric, m0, T=1.0, num_steps=10, phiinv=None, mommask=None, checkpoin
             for i in range(num_steps):
                 cur = _fused_step(metric, m0c, dt, cur, mk, ws, bufs[i % 2])
             return cur
+        if (num_steps > 0 and _needs_grad(m0, phiinv) and not _needs_grad(mommask)
+                and _fused_bwd_ok(metric, m0, phiinv, mommask)):
+            return EPDiffShootFunction.apply(metric, m0, dt, num_steps, phiinv, mommask, True)
         for i in range(num_steps):
             phiinv = EPDiff_step(metric, m0, dt, phiinv, mommask=mommask)
         return phiinv
