@@ -149,15 +149,20 @@ struct GSide {
   C* g;
   long long grs;
   int lvalid;
+  int lsplit = 1 << 30;  // lines l >= lsplit sit lskip words further on (the Nyquist line of a
+  int lskip = 0;         // cluster slab CTA); fft_stage only
 };
 
 // GSRC: the stage's inputs come from global memory instead of the tile; GDST: its outputs go to
 // global memory instead of the tile (used for the first / last stage of a pass, so the tile is
 // never filled or drained by a separate copy loop).
-template <typename R, int N, int BLOCK, int RAD, int L, bool INV, bool GSRC = false, bool GDST = false>
+// JSH / jump: tile row r lives (r >> JSH) * jump words further on than r*rs (a tile stored as panels
+// of 2^JSH rows, see the cluster slab kernels in fluid.cu); JSH = 0 means a plain tile.
+template <typename R, int N, int BLOCK, int RAD, int L, bool INV, bool GSRC = false, bool GDST = false, int JSH = 0>
 __device__ __forceinline__ void fft_stage(typename Cx<R>::T* tile, int rs, int ls,
                                           const typename Cx<R>::T* __restrict__ tw, int tid, int nth,
-                                          GSide<typename Cx<R>::T> gs = GSide<typename Cx<R>::T>()) {
+                                          GSide<typename Cx<R>::T> gs = GSide<typename Cx<R>::T>(),
+                                          int jump = 0) {
   using C = typename Cx<R>::T;
   constexpr int SUB = BLOCK / RAD;
   constexpr int ITEMS = L * (N / RAD);
@@ -167,7 +172,9 @@ __device__ __forceinline__ void fft_stage(typename Cx<R>::T* tile, int rs, int l
     const int blk = q / SUB, rest = q % SUB;
     const int row0 = blk * BLOCK + rest;
     C* p = tile + row0 * rs + l * ls;
-    C* gp = (GSRC || GDST) ? gs.g + (long long)row0 * gs.grs + l : nullptr;
+    // panel offset of tile row (row0 + n*SUB): compile-time per n in the outermost stage
+    auto jo = [&](int n) -> int { return JSH > 0 ? ((row0 + n * SUB) >> JSH) * jump : 0; };
+    C* gp = (GSRC || GDST) ? gs.g + (long long)row0 * gs.grs + l + (l >= gs.lsplit ? gs.lskip : 0) : nullptr;
     const bool ok = !(GSRC || GDST) || l < gs.lvalid;
     C x[RAD];
     if (!INV) {
@@ -179,7 +186,7 @@ __device__ __forceinline__ void fft_stage(typename Cx<R>::T* tile, int rs, int l
           if (ok) v = gp[(long long)n * SUB * gs.grs];
           x[n] = v;
         } else {
-          x[n] = p[n * SUB * rs];
+          x[n] = p[n * SUB * rs + jo(n)];
         }
       }
       reg_fft<RAD, false>(x);
@@ -191,7 +198,7 @@ __device__ __forceinline__ void fft_stage(typename Cx<R>::T* tile, int rs, int l
         if (GDST) {
           if (ok) gp[(long long)k * SUB * gs.grs] = v;
         } else {
-          p[k * SUB * rs] = v;
+          p[k * SUB * rs + jo(k)] = v;
         }
       }
     } else {
@@ -202,7 +209,7 @@ __device__ __forceinline__ void fft_stage(typename Cx<R>::T* tile, int rs, int l
           v.x = v.y = R(0);
           if (ok) v = gp[(long long)k * SUB * gs.grs];
         } else {
-          v = p[k * SUB * rs];
+          v = p[k * SUB * rs + jo(k)];
         }
         if (SUB > 1 && k != 0) v = cmulc(v, tw[rest * k * (N / BLOCK)]);
         x[k] = v;
@@ -213,7 +220,7 @@ __device__ __forceinline__ void fft_stage(typename Cx<R>::T* tile, int rs, int l
         if (GDST) {
           if (ok) gp[(long long)bitrev(i, BITS) * SUB * gs.grs] = x[i];
         } else {
-          p[bitrev(i, BITS) * SUB * rs] = x[i];
+          p[bitrev(i, BITS) * SUB * rs + jo(bitrev(i, BITS))] = x[i];
         }
       }
     }
@@ -458,9 +465,11 @@ __device__ __forceinline__ void unsplit_pair(C a, C b, C w, C& zk, C& zm) {
 }
 
 // twz: table of 2M entries e^{-2 pi i j / 2M}. Rows of the tile: element (r, l) at tile[r*rs + l*ls].
-template <typename R, int M, int L, bool INV>
+// JSH / jump as in fft_stage; nyq = offset of the Nyquist row (row M) in the tile, -1 = M*rs.
+template <typename R, int M, int L, bool INV, int JSH = 0>
 __device__ __forceinline__ void real_edge_stage(typename Cx<R>::T* tile, int rs, int ls,
-                                                const typename Cx<R>::T* __restrict__ twz, int tid, int nth) {
+                                                const typename Cx<R>::T* __restrict__ twz, int tid, int nth,
+                                                int jump = 0, int nyq = -1) {
   using C = typename Cx<R>::T;
   constexpr int bM = ilog2(M), ns = (bM + 3) / 4;
   constexpr int RAD = 1 << stage_bits(bM, ns - 1);
@@ -471,8 +480,10 @@ __device__ __forceinline__ void real_edge_stage(typename Cx<R>::T* tile, int rs,
     const int l = it % L, kl = it / L;
     const int klp = (NB - kl) % NB;
     const int b0 = fft_pos<NB>(kl), b1 = fft_pos<NB>(klp);
-    C* p0 = tile + (b0 * RAD) * rs + l * ls;
-    C* p1 = tile + (b1 * RAD) * rs + l * ls;
+    static_assert(JSH == 0 || (1 << JSH) % RAD == 0, "a radix block must not straddle panels");
+    C* p0 = tile + (b0 * RAD) * rs + l * ls + (JSH > 0 ? ((b0 * RAD) >> JSH) * jump : 0);
+    C* p1 = tile + (b1 * RAD) * rs + l * ls + (JSH > 0 ? ((b1 * RAD) >> JSH) * jump : 0);
+    C* pn = tile + (nyq < 0 ? M * rs : nyq) + l * ls;  // Nyquist word of this line
     C x[RAD], y[RAD];
     if (!INV) {
 #pragma unroll
@@ -483,7 +494,7 @@ __device__ __forceinline__ void real_edge_stage(typename Cx<R>::T* tile, int rs,
         x0.x = a.x + a.y; x0.y = R(0);
         xM.x = a.x - a.y; xM.y = R(0);
         p0[0] = x0;
-        tile[M * rs + l * ls] = xM;
+        *pn = xM;
 #pragma unroll
         for (int k2 = 1; k2 <= RAD / 2; ++k2) {
           C xk, xm;
@@ -514,7 +525,7 @@ __device__ __forceinline__ void real_edge_stage(typename Cx<R>::T* tile, int rs,
     } else {
       // unsplit Z'[k] = (Xk + conj Xm) + i conj(W^k)(Xk - conj Xm), then the inverse RAD-point stage
       if (kl == 0) {
-        const R r0 = p0[0].x, rM = tile[M * rs + l * ls].x;  // imaginary parts of DC / Nyquist ignored (C2R)
+        const R r0 = p0[0].x, rM = pn->x;  // imaginary parts of DC / Nyquist ignored (C2R)
         x[0].x = r0 + rM;
         x[0].y = r0 - rM;
 #pragma unroll

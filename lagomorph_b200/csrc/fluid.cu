@@ -22,6 +22,7 @@
 #include <mutex>
 #include <tuple>
 #include <vector>
+#include <cooperative_groups.h>
 #include "fft.cuh"
 
 namespace lgm {
@@ -405,6 +406,141 @@ slab_inv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec,
   for (int idx = tid; idx < Y * M; idx += kFftThreads) {
     const int y = idx / M, j = idx % M;
     o2[idx] = tile[j * P + y];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cluster slab (fp32, Y = Z = 256): the 256 x 129 spectrum slab of one (n, c, x) is 265 KB, more than
+// one SM's shared memory, so a thread-block CLUSTER of four CTAs owns it (69 KB each, 3 CTAs per SM
+// like the single-CTA slab kernels) and the transposition between the Z and the Y transform is an
+// all-to-all through distributed shared memory:
+//   Z phase : CTA r holds the real lines y in [64r, 64r+64) as tile[row(p)*P + yl] and transforms
+//             them along z. The 129 spectrum rows p are stored as four PANELS of 33 tile rows:
+//             panel q = rows p in [32q, 32q+32) plus one spare row; the spare row of panel 0 holds the
+//             Nyquist row p = 128.
+//   swap    : panel q of CTA r <-> panel r of CTA q (DSMEM), after which CTA r owns the spectrum rows
+//             of range r for ALL 256 lines: panel q now is (range r, y in [64q, 64q+64)).
+//   Y phase : 256-point transforms along y for its 32 lines (33 in CTA 0: the Nyquist line), the
+//             last stage stores straight to global memory.
+// Replaces zfwd + ypass (and ypass + zinv) at 256^3: one global round trip of the spectrum less in
+// each direction, 5 passes -> 3. (A two-CTA variant with 134 KB tiles, one CTA per SM, was measured
+// slower than the unfused passes: nothing overlaps the load phase.)
+// ------------------------------------------------------------------------------------------
+constexpr int kCsNC = 4;              // CTAs per cluster
+constexpr int kCsThreads = 256;
+constexpr int kCsYL = 256 / kCsNC;    // real lines per CTA in the Z phase (64)
+constexpr int kCsPR = 33;             // tile rows per panel
+constexpr int kCsP = kCsYL + 1;       // row pitch in complex words (65, odd: conflict free both ways)
+constexpr int kCsRows = kCsNC * kCsPR;
+constexpr int kCsNyq = 32 * kCsP;     // Nyquist row = spare row of panel 0
+constexpr int kCsJumpY = kCsPR * kCsP - kCsYL;  // Y phase: line y lives in panel y >> 6
+
+// panel q of rank r <-> panel r of rank q; every (row, yl) element pair is moved by exactly one thread
+// (rows of parity [r < q] by the lower rank, the others by the higher rank).
+__device__ __forceinline__ void cslab_swap(float2* tile, unsigned rank, int tid) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+  for (unsigned d = 1; d < kCsNC; ++d) {
+    const unsigned q = (rank + d) % kCsNC;
+    float2* mine = tile + q * kCsPR * kCsP;
+    float2* theirs = cluster.map_shared_rank(tile, q) + rank * kCsPR * kCsP;
+    const int par = (rank < q) ? 0 : 1;
+#pragma unroll 4
+    for (int e = tid; e < 17 * kCsYL; e += kCsThreads) {
+      const int i = 2 * (e / kCsYL) + par, yl = e % kCsYL;
+      if (i < kCsPR) {
+        const int o = i * kCsP + yl;
+        const float2 a = mine[o], b = theirs[o];
+        mine[o] = b;
+        theirs[o] = a;
+      }
+    }
+  }
+}
+
+template <bool INV, int L>
+__device__ __forceinline__ void cslab_ypass(float2* tile, const float2* twy, int tid, GSide<float2> g) {
+  constexpr int Y = 256;
+  if (!INV) {
+    fft_stage<float, Y, Y, 16, L, false, false, false, 6>(tile, 1, kCsP, twy, tid, kCsThreads, GSide<float2>(), kCsJumpY);
+    __syncthreads();
+    fft_stage<float, Y, 16, 16, L, false, false, true, 6>(tile, 1, kCsP, twy, tid, kCsThreads, g, kCsJumpY);
+  } else {
+    fft_stage<float, Y, 16, 16, L, true, true, false, 6>(tile, 1, kCsP, twy, tid, kCsThreads, g, kCsJumpY);
+    __syncthreads();
+    fft_stage<float, Y, Y, 16, L, true, false, false, 6>(tile, 1, kCsP, twy, tid, kCsThreads, GSide<float2>(), kCsJumpY);
+  }
+}
+
+__global__ void __cluster_dims__(kCsNC, 1, 1) __launch_bounds__(kCsThreads, 3)
+cslab_fwd_kernel(float2* __restrict__ spec, const float* __restrict__ in, const float2* __restrict__ twz_g,
+                 const float2* __restrict__ twy_g) {
+  namespace cg = cooperative_groups;
+  constexpr int Y = 256, Z = 256, M = Z / 2, ZC = M + 1, P = kCsP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tile = reinterpret_cast<float2*>(smem_raw);  // kCsRows x P
+  float2* twz = tile + kCsRows * P;                    // Z entries
+  float2* twM = twz + Z;                               // M entries
+  float2* twy = twM + M;                               // Y entries
+  const int tid = threadIdx.x;
+  const unsigned rank = cg::this_cluster().block_rank();
+  const size_t slab = blockIdx.x / kCsNC;
+  for (int j = tid; j < Z; j += kCsThreads) twz[j] = twz_g[j];
+  for (int j = tid; j < M; j += kCsThreads) twM[j] = twz_g[2 * j];
+  for (int j = tid; j < Y; j += kCsThreads) twy[j] = twy_g[j];
+  const float2* in2 = reinterpret_cast<const float2*>(in) + (slab * Y + rank * kCsYL) * M;
+#pragma unroll kSlabIoUnroll
+  for (int idx = tid; idx < kCsYL * M; idx += kCsThreads) {
+    const int yl = idx / M, j = idx % M;
+    tile[(j + (j >> 5)) * P + yl] = in2[idx];
+  }
+  __syncthreads();
+  // Z: half-length complex FFT (16 x 8) with the real split fused into its last stage, on panel rows
+  fft_stage<float, M, M, 16, kCsYL, false, false, false, 5>(tile, P, 1, twM, tid, kCsThreads, GSide<float2>(), P);
+  __syncthreads();
+  real_edge_stage<float, M, kCsYL, false, 5>(tile, P, 1, twz, tid, kCsThreads, P, kCsNyq);
+  cg::this_cluster().sync();
+  cslab_swap(tile, rank, tid);
+  cg::this_cluster().sync();
+  // Y transform over the four panels; the last stage stores straight to the spectrum slab [ry][rz]
+  GSide<float2> gout{spec + slab * Y * ZC + rank * 32, ZC, rank == 0 ? 33 : 32, 32, M - 32};
+  if (rank == 0) cslab_ypass<false, 33>(tile, twy, tid, gout);
+  else cslab_ypass<false, 32>(tile, twy, tid, gout);
+}
+
+__global__ void __cluster_dims__(kCsNC, 1, 1) __launch_bounds__(kCsThreads, 3)
+cslab_inv_kernel(float* __restrict__ out, const float2* __restrict__ spec, const float2* __restrict__ twz_g,
+                 const float2* __restrict__ twy_g) {
+  namespace cg = cooperative_groups;
+  constexpr int Y = 256, Z = 256, M = Z / 2, ZC = M + 1, P = kCsP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tile = reinterpret_cast<float2*>(smem_raw);
+  float2* twz = tile + kCsRows * P;
+  float2* twM = twz + Z;
+  float2* twy = twM + M;
+  const int tid = threadIdx.x;
+  const unsigned rank = cg::this_cluster().block_rank();
+  const size_t slab = blockIdx.x / kCsNC;
+  for (int j = tid; j < Z; j += kCsThreads) twz[j] = twz_g[j];
+  for (int j = tid; j < M; j += kCsThreads) twM[j] = twz_g[2 * j];
+  for (int j = tid; j < Y; j += kCsThreads) twy[j] = twy_g[j];
+  __syncthreads();
+  GSide<float2> gin{const_cast<float2*>(spec) + slab * Y * ZC + rank * 32, ZC, rank == 0 ? 33 : 32, 32, M - 32};
+  if (rank == 0) cslab_ypass<true, 33>(tile, twy, tid, gin);
+  else cslab_ypass<true, 32>(tile, twy, tid, gin);
+  cg::this_cluster().sync();
+  cslab_swap(tile, rank, tid);
+  cg::this_cluster().sync();
+  real_edge_stage<float, M, kCsYL, true, 5>(tile, P, 1, twz, tid, kCsThreads, P, kCsNyq);
+  __syncthreads();
+  fft_stage<float, M, M, 16, kCsYL, true, false, false, 5>(tile, P, 1, twM, tid, kCsThreads, GSide<float2>(), P);
+  __syncthreads();
+  float2* o2 = reinterpret_cast<float2*>(out) + (slab * Y + rank * kCsYL) * M;
+#pragma unroll 4
+  for (int idx = tid; idx < kCsYL * M; idx += kCsThreads) {
+    const int yl = idx / M, j = idx % M;
+    o2[idx] = tile[(j + (j >> 5)) * P + yl];
   }
 }
 
@@ -844,10 +980,30 @@ static int slab_launch(bool inv, void* real, typename Cx<R>::T* spec, long long 
   }
   return LGM_OK;
 }
+// 256 x 256 slabs (fp32): four-CTA cluster kernels, see cslab_fwd_kernel.
+static int cslab_launch(bool inv, void* real, float2* spec, long long slabs, const FluidPlan& p, cudaStream_t s) {
+  static const bool off = getenv("LGM_NO_CLUSTER_SLAB") != nullptr;  // kernel experiments only
+  if (off) return LGM_EUNSUP;
+  const size_t smem = sizeof(float2) * ((size_t)kCsRows * kCsP + 256 + 128 + 256);
+  if (!inv) {
+    LGM_CUDA_TRY(set_smem(cslab_fwd_kernel, smem), "cslab_fwd smem");
+    cslab_fwd_kernel<<<(unsigned)(kCsNC * slabs), kCsThreads, smem, s>>>(spec, (const float*)real, (const float2*)p.tw[2], (const float2*)p.tw[1]);
+    count_launch("slab_fwd", s);
+  } else {
+    LGM_CUDA_TRY(set_smem(cslab_inv_kernel, smem), "cslab_inv smem");
+    cslab_inv_kernel<<<(unsigned)(kCsNC * slabs), kCsThreads, smem, s>>>((float*)real, spec, (const float2*)p.tw[2], (const float2*)p.tw[1]);
+    count_launch("slab_inv", s);
+  }
+  return LGM_OK;
+}
+
 template <typename R>
 static int slab_pass(bool inv, int Y, int Z, void* real, typename Cx<R>::T* spec, long long slabs,
                      const FluidPlan& p, cudaStream_t s) {
   if (Y != Z) return LGM_EUNSUP;
+  if constexpr (sizeof(R) == 4) {
+    if (Y == 256) return cslab_launch(inv, real, spec, slabs, p, s);
+  }
   switch (Y) {
     case 16: return slab_launch<R, 16>(inv, real, spec, slabs, p, s);
     case 32: return slab_launch<R, 32>(inv, real, spec, slabs, p, s);

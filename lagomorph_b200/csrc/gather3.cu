@@ -15,6 +15,9 @@
 // instructions; floor() is a magic-number add.
 #include "gather_common.cuh"
 
+#ifndef LGM_ADSTAR_MINB
+#define LGM_ADSTAR_MINB 4  /* CTAs/SM the Ad_star instantiation is compiled for (64 registers) */
+#endif
 #ifndef LGM_GATHER_BX
 #define LGM_GATHER_BX 1  /* 2,4,8 measured equal on B200: the gathers are L1-data-pipe bound, not L2 bound */
 #endif
@@ -24,7 +27,7 @@ namespace lgm {
 // MODE 0: Ad_star (a = phiinv, b = m0); MODE 1: compose (a = u, b = v).
 // blockDim = (32, 8): a warp walks one z row (lane = z, NV chunks of 32), a CTA covers 8 y rows.
 template <int MODE, int NV, int BX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MODE == 0 ? LGM_ADSTAR_MINB : 5)
 gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
                int X, int Y, int Z, float dh, float dl, float dsr, float dtr) {
   // blockDim = (32, 8/BX, BX): BX neighbouring x slabs share a CTA so that the upper-x corner rows
@@ -41,9 +44,18 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
   const float* bn1 = bn + V;
   const float* bn2 = bn1 + V;
   float* on = out + (size_t)n * 3 * V;
-  // keep the per-subject channel bases as plain 64-bit registers so that every gather address is
-  // one IMAD.WIDE.U32 (base + 4*index) instead of a 64-bit add chain
+  float* on1 = on + V;
+  float* on2 = on1 + V;
+  const float* an1 = an + V;
+  const float* an2 = an1 + V;
+  // keep the per-subject channel bases as plain 64-bit registers so that every address (gather,
+  // stencil neighbour, store) is ONE IMAD.WIDE (base + 4*index) on a 32-bit in-volume index instead
+  // of a 64-bit add / LEA chain (the stencil loads alone were 4 address instructions each)
   asm volatile("" : "+l"(bn), "+l"(bn1), "+l"(bn2));
+  asm volatile("" : "+l"(an), "+l"(an1), "+l"(an2));
+  asm volatile("" : "+l"(on), "+l"(on1), "+l"(on2));
+  const unsigned four = opaque_four();
+  const float hiX = (float)X - 0.5f, hiY = (float)Y - 0.5f, hiZ = (float)Z - 0.5f;
   const int row = i * sx + j * sy;
   const float fi = (float)i, fj = (float)j;
   const int xm = (i > 0) ? -sx : 0, xp = (i < X - 1) ? sx : 0;
@@ -55,10 +67,9 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
   for (int v = 0; v < NV; ++v) {
     const int k = (blockIdx.x * NV + v) * 32 + threadIdx.x;
     if (k < Z) {
-      const float* a0 = an + (row + k);
-      Apre[v][0] = __ldg(a0);
-      Apre[v][1] = __ldg(a0 + V);
-      Apre[v][2] = __ldg(a0 + 2 * V);
+      Apre[v][0] = __ldg(an + (row + k));  // literal addressing: must not wait for `four`
+      Apre[v][1] = __ldg(an1 + (row + k));
+      Apre[v][2] = __ldg(an2 + (row + k));
     }
   }
 #pragma unroll
@@ -66,9 +77,6 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
     const int k = (blockIdx.x * NV + v) * 32 + threadIdx.x;
     if (k >= Z) break;
     const int c0 = row + k;
-    const float* a0 = an + c0;
-    const float* a1 = a0 + V;
-    const float* a2 = a1 + V;
     const float A0 = Apre[v][0], A1 = Apre[v][1], A2 = Apre[v][2];
     float hx, hy, hz;
     const float fk = (float)k;
@@ -81,7 +89,7 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
       hy = coord_f32(fj, A1, dh, dl);
       hz = coord_f32(fk, A2, dh, dl);
     }
-    const Ax3 ax = axis_fast(hx, X), ay = axis_fast(hy, Y), az = axis_fast(hz, Z);
+    const Ax3 ax = axis_fwd(hx, X, hiX), ay = axis_fwd(hy, Y, hiY), az = axis_fwd(hz, Z, hiZ);
     int zs;
     float wv;
     z_pair(az, Z, zs, wv);
@@ -89,25 +97,27 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
     const unsigned ry0 = ay.i0 * sy, ry1 = ay.i1 * sy;
     const unsigned i00 = rx0 + ry0, i01 = rx0 + ry1, i10 = rx1 + ry0, i11 = rx1 + ry1;
     const float omt = 1.f - ax.t, omu = 1.f - ay.t, omv = 1.f - wv;
-    const float m0v = trilerp(bn, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv);
-    const float m1v = trilerp(bn1, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv);
-    const float m2v = trilerp(bn2, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv);
+    const float m0v = trilerp(bn, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv, four);
+    const float m1v = trilerp(bn1, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv, four);
+    const float m2v = trilerp(bn2, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv, four);
     if (MODE == 1) {
-      on[c0] = __fadd_rn(__fmul_rn(dsr, A0), __fmul_rn(dtr, m0v));
-      on[c0 + V] = __fadd_rn(__fmul_rn(dsr, A1), __fmul_rn(dtr, m1v));
-      on[c0 + 2 * V] = __fadd_rn(__fmul_rn(dsr, A2), __fmul_rn(dtr, m2v));
+      *at4(on, c0, four) = __fadd_rn(__fmul_rn(dsr, A0), __fmul_rn(dtr, m0v));
+      *at4(on1, c0, four) = __fadd_rn(__fmul_rn(dsr, A1), __fmul_rn(dtr, m1v));
+      *at4(on2, c0, four) = __fadd_rn(__fmul_rn(dsr, A2), __fmul_rn(dtr, m2v));
     } else {
-      const int zm = (k > 0) ? -1 : 0, zp = (k < Z - 1) ? 1 : 0;
-      const float* ac[3] = {a0, a1, a2};
+      const int ixp = c0 + xp, ixm = c0 + xm, iyp = c0 + yp, iym = c0 + ym;
+      const int izp = c0 + ((k < Z - 1) ? 1 : 0), izm = c0 - ((k > 0) ? 1 : 0);
+      const float* ac[3] = {an, an1, an2};
+      float* oc[3] = {on, on1, on2};
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float g0 = 0.5f * (__ldg(ac[c] + xp) - __ldg(ac[c] + xm));
-        float g1 = 0.5f * (__ldg(ac[c] + yp) - __ldg(ac[c] + ym));
-        float g2 = 0.5f * (__ldg(ac[c] + zp) - __ldg(ac[c] + zm));
+        float g0 = 0.5f * (__ldg(at4(ac[c], ixp, four)) - __ldg(at4(ac[c], ixm, four)));
+        float g1 = 0.5f * (__ldg(at4(ac[c], iyp, four)) - __ldg(at4(ac[c], iym, four)));
+        float g2 = 0.5f * (__ldg(at4(ac[c], izp, four)) - __ldg(at4(ac[c], izm, four)));
         if (c == 0) g0 += 1.f;
         if (c == 1) g1 += 1.f;
         if (c == 2) g2 += 1.f;
-        on[c0 + c * V] = g0 * m0v + g1 * m1v + g2 * m2v;  // diff.cu:118-120
+        *at4(oc[c], c0, four) = g0 * m0v + g1 * m1v + g2 * m2v;  // diff.cu:118-120
       }
     }
   }
@@ -129,6 +139,8 @@ interp3_kernel(float* __restrict__ out, const float* __restrict__ I, const float
   const float* In = I + (size_t)n * I_batch_stride;
   float* on = out + (size_t)n * C * V;
   asm volatile("" : "+l"(In));
+  const unsigned four = opaque_four();
+  const float hiX = (float)X - 0.5f, hiY = (float)Y - 0.5f, hiZ = (float)Z - 0.5f;
   const int row = i * sx + j * sy;
   const float fi = (float)i, fj = (float)j;
 #pragma unroll
@@ -148,7 +160,7 @@ interp3_kernel(float* __restrict__ out, const float* __restrict__ I, const float
       hy = coord_f32(fj, A1, dh, dl);
       hz = coord_f32(fk, A2, dh, dl);
     }
-    const Ax3 ax = axis_fast(hx, X), ay = axis_fast(hy, Y), az = axis_fast(hz, Z);
+    const Ax3 ax = axis_fwd(hx, X, hiX), ay = axis_fwd(hy, Y, hiY), az = axis_fwd(hz, Z, hiZ);
     int zs;
     float wv;
     z_pair(az, Z, zs, wv);
@@ -159,7 +171,7 @@ interp3_kernel(float* __restrict__ out, const float* __restrict__ I, const float
     const float* Ic = In;
     float* oc = on + c0;
     for (int c = 0; c < C; ++c, Ic += V, oc += V)
-      *oc = trilerp(Ic, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv);
+      *oc = trilerp(Ic, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv, four);
   }
 }
 

@@ -41,16 +41,49 @@ __device__ __forceinline__ Ax3 axis_fast(float x, int n) {
   return a;
 }
 
+// Cheaper twin of axis_fast() for the forward gather kernels. The coordinate is clamped to
+// [-1, n - 1/2] (outside of it both corners are the border voxel and the result is the border value for
+// any weight, see z_pair()), floor() is ONE round-down add of the magic number, and the clamps of the
+// two corner indices shrink to one instruction each because floor is already in [-1, n-1].
+__device__ __forceinline__ Ax3 axis_fwd(float x, int n, float hi) {  // hi = n - 0.5f
+  Ax3 a;
+  x = fminf(fmaxf(x, -1.f), hi);
+  const float r = __fadd_rd(x, 12582912.f);  // floor(x) + 1.5 * 2^23, exact
+  const int f = __float_as_int(r) - 0x4B400000;
+  a.t = x - __fsub_rn(r, 12582912.f);
+  a.i0 = max(f, 0);
+  a.i1 = min(f + 1, n - 1);
+  return a;
+}
+
+// base + 4*idx as ONE IMAD.WIDE.U32 whose multiplier lives in a register for the whole kernel. With
+// a literal 4 and the (uniform) base in a uniform register ptxas has to materialise the constant with
+// a MOV in front of every address: 10 % of the gather kernels' issue slots. An empty asm() does not
+// hide the constant from ptxas, a load from a mutable __device__ word does (one LDG per thread).
+// (indexed by the lane so that the load is not uniform: a uniform-register copy would again be MOVed
+// into a vector register at every use)
+static __device__ unsigned g_four[32] = {4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+                                         4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
+__device__ __forceinline__ unsigned opaque_four() { return g_four[threadIdx.x & 31]; }
+template <typename T>
+__device__ __forceinline__ T* at4(T* base, unsigned idx, unsigned four) {
+  return (T*)((char*)base + (unsigned long long)idx * four);
+}
+template <typename T>
+__device__ __forceinline__ const T* at4(const T* base, unsigned idx, unsigned four) {
+  return (const T*)((const char*)base + (unsigned long long)idx * four);
+}
+
 // 8-corner gather + nested lerp (corner numbering / evaluation order of include/interp.h:91-122).
 // i00..i11 are the element indices of the four (x,y) corner rows at the lower z corner; the upper z
 // corner is always the +1 neighbour (an immediate offset on the same address register), see z_pair().
 __device__ __forceinline__ float trilerp(const float* __restrict__ img, unsigned i00, unsigned i01,
                                          unsigned i10, unsigned i11, float t, float u, float v,
-                                         float omt, float omu, float omv) {
-  const float* p00 = img + i00;
-  const float* p01 = img + i01;
-  const float* p10 = img + i10;
-  const float* p11 = img + i11;
+                                         float omt, float omu, float omv, unsigned four) {
+  const float* p00 = at4(img, i00, four);
+  const float* p01 = at4(img, i01, four);
+  const float* p10 = at4(img, i10, four);
+  const float* p11 = at4(img, i11, four);
   float v0 = __ldg(p00), v4 = __ldg(p00 + 1);
   float v3 = __ldg(p01), v7 = __ldg(p01 + 1);
   float v1 = __ldg(p10), v5 = __ldg(p10 + 1);

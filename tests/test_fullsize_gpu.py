@@ -120,3 +120,16 @@ def test_extreme_displacements_and_ragged_sizes(lm, orc):
     adj = lm.interp_adjoint(I.cuda(), un.cuda())
     torch.cuda.synchronize()
     assert torch.isfinite(out[0, :, 0, 0, 0]).all()
+
+
+@pytest.mark.parametrize("params", [[0.1, 0.0, 0.01], [0.1, 0.01, 0.001]])
+def test_fluid_metric_256_matches_oracle(lm, orc, params):
+    """256^3 takes the two-CTA cluster slab kernels (DSMEM transposition between the Z and the Y
+    transform): sharp and flat against the CPU oracle (torch.fft), tolerance 1e-5 relative L2."""
+    sh = (1, 3, 256, 256, 256)
+    m = torch.randn(sh, generator=torch.Generator().manual_seed(21))
+    om, gm = orc.FluidMetric(params), lm.FluidMetric(params)
+    for name in ("sharp", "flat"):
+        ref = getattr(om, name)(m)
+        out = getattr(gm, name)(m.cuda()).cpu()
+        assert ((out - ref).norm() / ref.norm()).item() <= 1e-5, name
