@@ -227,6 +227,32 @@ __device__ __forceinline__ void fft_stage(typename Cx<R>::T* tile, int rs, int l
   }
 }
 
+// Innermost forward stage, a per-element multiplier and the innermost inverse stage fused in
+// registers. The last forward stage (BLOCK == RAD) transforms RAD consecutive tile rows of one line;
+// the first executed inverse stage reads exactly those rows again, so a Fourier multiplier that sits
+// between the two transforms (the X pass of the fluid operator) needs no shared-memory round trip
+// and no barrier on either side of it: rows in -> DFT -> mult(row, v) -> inverse DFT -> rows out.
+// Arithmetic and its order are those of the three separate steps (bit-identical results).
+template <typename R, int N, int RAD, int L, typename F>
+__device__ __forceinline__ void fft_mid_stage(typename Cx<R>::T* tile, int rs, int ls, int tid, int nth, F mult) {
+  using C = typename Cx<R>::T;
+  constexpr int ITEMS = L * (N / RAD);
+  constexpr int BITS = ilog2(RAD);
+  for (int it = tid; it < ITEMS; it += nth) {
+    const int l = it % L, blk = it / L;
+    C* p = tile + blk * RAD * rs + l * ls;
+    C x[RAD], y[RAD];
+#pragma unroll
+    for (int n = 0; n < RAD; ++n) x[n] = p[n * rs];
+    reg_fft<RAD, false>(x);  // x[i] = frequency row blk*RAD + bitrev(i)
+#pragma unroll
+    for (int k = 0; k < RAD; ++k) y[k] = mult(blk * RAD + k, l, x[bitrev(k, BITS)]);
+    reg_fft<RAD, true>(y);
+#pragma unroll
+    for (int i = 0; i < RAD; ++i) p[bitrev(i, BITS) * rs] = y[i];
+  }
+}
+
 // Outermost stage (BLOCK == N) with one side in GLOBAL memory: the forward transform's first
 // stage reads its RAD inputs straight from global memory (row stride grs, lanes along l are
 // consecutive words => coalesced) and stores to the shared tile; the inverse transform's last

@@ -740,6 +740,41 @@ xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
     }
   }
   __syncthreads();
+  constexpr int NS = (ilog2(NX) + 3) / 4;  // radix stages of the X transform
+  if constexpr (NCH == 1 && NS >= 2) {
+    // beta == 0: forward -> scalar multiplier -> inverse with the innermost stage pair and the
+    // multiplier fused in registers (fft_mid_stage): 2 shared-memory round trips and 2 barriers for
+    // a two-stage transform instead of 4 and 4.
+    constexpr int RAD0 = 1 << stage_bits(ilog2(NX), 0);
+    constexpr int RADL = 1 << stage_bits(ilog2(NX), NS - 1);
+    fft_stage_edge<R, NX, RAD0, T, false>(base, plane, tile, T, 1, tw, lvalid, tid, kFftThreads);
+    __syncthreads();
+    if constexpr (NS > 2) {
+      ColFFT<R, NX, NX / RAD0, 1, T>::fwd_nolast(tile, T, 1, tw, tid, kFftThreads);
+      __syncthreads();
+    }
+    fft_mid_stage<R, NX, RADL, T>(tile, T, 1, tid, kFftThreads, [&](int r, int, C v) -> C {
+      const R sw = (D == 2) ? (lx[r] + wy) : (lx[r] + wy + wz);
+      const R lambda = (R)(gamma + alpha * (double)sw);
+      const R Lm = lambda * lambda;
+      if (INVERSE) {
+        const R f = oo_sqrt_fast<R>(Lm);
+        v.x = ((v.x * f) * f) * scale;
+        v.y = ((v.y * f) * f) * scale;
+      } else {
+        v.x = (Lm * v.x) * scale;
+        v.y = (Lm * v.y) * scale;
+      }
+      return v;
+    });
+    __syncthreads();
+    if constexpr (NS > 2) {
+      ColFFT<R, NX, NX / RAD0, 1, T>::inv_nolast(tile, T, 1, tw, tid, kFftThreads);
+      __syncthreads();
+    }
+    fft_stage_edge<R, NX, RAD0, T, true>(base, plane, tile, T, 1, tw, lvalid, tid, kFftThreads);
+    return;
+  }
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch)
     col_fft_fwd_from_global<R, NX, T>(base + (long long)ch * NX * plane, plane, tile + ch * NX * T, T, 1, tw,
