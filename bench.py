@@ -234,7 +234,7 @@ def main():
             h_host = torch.empty((batch, 3) + tuple(shape), dtype=torch.float32).pin_memory()
             def e2e_step():
                 # public host-buffer API: pipelined H2D / shoot / D2H over chunks of subjects
-                lm.expmap_host(metric, m_host, num_steps=nsteps, out=h_host, device=dev, chunk=int(os.environ.get("LGM_E2E_CHUNK", "3")))
+                lm.expmap_host(metric, m_host, num_steps=nsteps, out=h_host, device=dev)
             for _ in range(min(W, 2)):
                 e2e_step()
             barrier()

@@ -595,6 +595,88 @@ __device__ __forceinline__ void real_edge_stage(typename Cx<R>::T* tile, int rs,
   }
 }
 
+// Outermost stage of the Z (contiguous-axis) transform with its global side along the LINE: the L
+// lines of M complex words are rows of a row-major global array (line stride = M words), the tile is
+// transposed (element (r, l) at tile[r*rs + l], l = line). Lanes run over `rest` first (consecutive
+// words of one line: SUB*8-byte runs, every fetched sector fully used) and then over lines spaced SUB
+// apart, which with a pitch rs = 1 (mod 16) makes the 64-bit shared-memory accesses of every
+// half-warp hit 16 distinct bank pairs. Forward: global -> registers -> tile; inverse: tile ->
+// registers -> global. Removes the separate fill / drain loop of the Z passes (one shared-memory
+// write + read of the whole tile). Needs L % 32 == 0. JSH / jump as in fft_stage.
+template <typename R, int M, int RAD, int L, bool INV, int JSH = 0>
+__device__ __forceinline__ void zedge_stage(typename Cx<R>::T* __restrict__ g, typename Cx<R>::T* tile, int rs,
+                                            const typename Cx<R>::T* __restrict__ tw, int tid, int nth,
+                                            int jump = 0) {
+  using C = typename Cx<R>::T;
+  constexpr int SUB = M / RAD;
+  constexpr int W = SUB < 32 ? 32 / SUB : 1;   // lines per warp
+  constexpr int BITS = ilog2(RAD);
+  static_assert(L % 32 == 0 && (SUB >= 32 || 32 % SUB == 0), "zedge_stage: L must be a multiple of 32");
+  for (int it = tid; it < L * SUB; it += nth) {
+    const int rest = it % SUB, slot = it / SUB;
+    const int l = (SUB < 32) ? (slot / 32) * 32 + (slot % W) * SUB + (slot % 32) / W : slot;
+    C* gp = g + (size_t)l * M + rest;
+    C* p = tile + rest * rs + l;
+    auto jo = [&](int n) -> int { return JSH > 0 ? ((rest + n * SUB) >> JSH) * jump : 0; };
+    C x[RAD];
+    if (!INV) {
+#pragma unroll
+      for (int n = 0; n < RAD; ++n) x[n] = gp[n * SUB];
+      reg_fft<RAD, false>(x);
+#pragma unroll
+      for (int i = 0; i < RAD; ++i) {
+        const int k = bitrev(i, BITS);
+        C v = x[i];
+        if (k != 0) v = cmul(v, tw[rest * k]);
+        p[k * SUB * rs + jo(k)] = v;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < RAD; ++k) {
+        C v = p[k * SUB * rs + jo(k)];
+        if (k != 0) v = cmulc(v, tw[rest * k]);
+        x[k] = v;
+      }
+      reg_fft<RAD, true>(x);
+#pragma unroll
+      for (int i = 0; i < RAD; ++i) gp[bitrev(i, BITS) * SUB] = x[i];
+    }
+  }
+}
+
+// Real transforms with the outermost stage on global memory (see zedge_stage): `g` points to the L
+// real lines (2M reals = M complex words each). Forward leaves the half spectrum in the tile rows
+// 0..M; the inverse consumes it and writes the real lines. Requires >= 2 radix stages.
+template <typename R, int M, int L>
+__device__ __forceinline__ void real_fft_fwd_g(const R* g, typename Cx<R>::T* tile, int rs,
+                                               const typename Cx<R>::T* twM, const typename Cx<R>::T* twz,
+                                               int tid, int nth) {
+  using C = typename Cx<R>::T;
+  constexpr int RAD0 = 1 << stage_bits(ilog2(M), 0);
+  static_assert((ilog2(M) + 3) / 4 >= 2, "real_fft_fwd_g needs two radix stages");
+  zedge_stage<R, M, RAD0, L, false>(reinterpret_cast<C*>(const_cast<R*>(g)), tile, rs, twM, tid, nth);
+  __syncthreads();
+  if constexpr (!ColFFT<R, M, M / RAD0, 1, L>::LASTSTAGE) {
+    ColFFT<R, M, M / RAD0, 1, L>::fwd_nolast(tile, rs, 1, twM, tid, nth);
+    __syncthreads();
+  }
+  real_edge_stage<R, M, L, false>(tile, rs, 1, twz, tid, nth);
+}
+template <typename R, int M, int L>
+__device__ __forceinline__ void real_fft_inv_g(R* g, typename Cx<R>::T* tile, int rs,
+                                               const typename Cx<R>::T* twM, const typename Cx<R>::T* twz,
+                                               int tid, int nth) {
+  using C = typename Cx<R>::T;
+  constexpr int RAD0 = 1 << stage_bits(ilog2(M), 0);
+  real_edge_stage<R, M, L, true>(tile, rs, 1, twz, tid, nth);
+  __syncthreads();
+  if constexpr (!ColFFT<R, M, M / RAD0, 1, L>::LASTSTAGE) {
+    ColFFT<R, M, M / RAD0, 1, L>::inv_nolast(tile, rs, 1, twM, tid, nth);
+    __syncthreads();
+  }
+  zedge_stage<R, M, RAD0, L, true>(reinterpret_cast<C*>(g), tile, rs, twM, tid, nth);
+}
+
 // real forward: tile rows 0..M-1 hold z[j] = (x[2j], x[2j+1]); on return rows 0..M hold the half
 // spectrum in storage order (row M = Nyquist). twM: e^{-2 pi i j / M} (M entries).
 template <typename R, int M, int L>

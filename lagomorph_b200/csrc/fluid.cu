@@ -272,6 +272,14 @@ constexpr int kSlabIoUnroll = LGM_SLAB_IO_UNROLL;
 #define LGM_XPASS_MINBLOCKS 4  /* 64 registers: measured 0.254 -> 0.240 ms per C2 X pass vs 80 registers */
 #endif
 
+// Z transforms whose outermost radix stage works on global memory (fft.cuh zedge_stage): needs two
+// radix stages and a multiple of 32 lines per CTA.
+#ifndef LGM_ZEDGE
+#define LGM_ZEDGE 1
+#endif
+template <int M, int L>
+constexpr bool kZEdge = LGM_ZEDGE && ((ilog2(M) + 3) / 4 >= 2) && (L % 32 == 0);
+
 // Z forward: L real lines of Z points -> L spectrum lines of Z/2+1 words.
 template <typename R, int Z, int L>
 __global__ void __launch_bounds__(kFftThreads)
@@ -285,24 +293,29 @@ zfwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in, long
   const int tid = threadIdx.x;
   const long long row0 = (long long)blockIdx.x * L;
   for (int j = tid; j < Z; j += kFftThreads) tw[j] = tw_g[j];
-  const C* in2 = reinterpret_cast<const C*>(in);
+  C* twM = tw + Z;  // M entries W_M^j = W_Z^{2j}, compacted (fft_stage indexes tw[j*(M/BLOCK)])
+  for (int j = tid; j < M; j += kFftThreads) twM[j] = tw_g[2 * j];
+  bool edge = false;
+  if constexpr (kZEdge<M, L>) edge = (row0 + L <= rows_total);
+  if (edge) {
+    if constexpr (kZEdge<M, L>) {
+      __syncthreads();
+      real_fft_fwd_g<R, M, L>(in + row0 * Z, tile, P, twM, tw, tid, kFftThreads);
+    }
+  } else {
+    const C* in2 = reinterpret_cast<const C*>(in);
 #pragma unroll kSlabIoUnroll
-  for (int idx = tid; idx < L * M; idx += kFftThreads) {
-    const int l = idx / M, j = idx % M;
-    C v;
-    v.x = v.y = R(0);
-    if (row0 + l < rows_total) v = in2[(row0 + l) * M + j];
-    tile[j * P + l] = v;
+    for (int idx = tid; idx < L * M; idx += kFftThreads) {
+      const int l = idx / M, j = idx % M;
+      C v;
+      v.x = v.y = R(0);
+      if (row0 + l < rows_total) v = in2[(row0 + l) * M + j];
+      tile[j * P + l] = v;
+    }
+    __syncthreads();
+    // half-length complex FFT with the real split fused into its last radix stage (fft.cuh)
+    real_fft_fwd<R, M, L>(tile, P, 1, twM, tw, tid, kFftThreads);
   }
-  __syncthreads();
-  // half-length complex FFT; its twiddles W_M^j = W_Z^{2j}: pass a strided view via a table
-  // of M entries built in place over the first half would alias, so use stride-2 reads.
-  // (fft_stage indexes tw[j*(M/BLOCK)], so hand it a table compacted to M entries.)
-  C* twM = tw + Z;  // M entries, compacted
-  for (int j = tid; j < M; j += kFftThreads) twM[j] = tw[2 * j];
-  __syncthreads();
-  // half-length complex FFT with the real split fused into its last radix stage (fft.cuh)
-  real_fft_fwd<R, M, L>(tile, P, 1, twM, tw, tid, kFftThreads);
   __syncthreads();
   for (int idx = tid; idx < L * (M + 1); idx += kFftThreads) {
     const int l = idx / (M + 1), p = idx % (M + 1);
@@ -334,6 +347,8 @@ zinv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec, lon
     tile[p * P + l] = v;
   }
   __syncthreads();
+  // (storing the last radix stage straight to global memory, as zfwd loads its first one, was
+  // measured slower here: 64-byte store runs, 0.65 -> 0.69 ms at 256^3 x 8)
   // unsplit fused into the first radix stage of the inverse half-length FFT (fft.cuh)
   real_fft_inv<R, M, L>(tile, P, 1, twM, tw, tid, kFftThreads);
   __syncthreads();
@@ -364,14 +379,20 @@ slab_fwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in,
   for (int j = tid; j < Z; j += kFftThreads) twz[j] = twz_g[j];
   for (int j = tid; j < M; j += kFftThreads) twM[j] = twz_g[2 * j];
   for (int j = tid; j < Y; j += kFftThreads) twy[j] = twy_g[j];
-  const C* in2 = reinterpret_cast<const C*>(in) + (size_t)blockIdx.x * Y * M;
+  if constexpr (kZEdge<M, Y>) {
+    // Z: first radix stage straight from global memory (no fill loop), then the fused split stage
+    __syncthreads();
+    real_fft_fwd_g<R, M, Y>(in + (size_t)blockIdx.x * Y * Z, tile, P, twM, twz, tid, kFftThreads);
+  } else {
+    const C* in2 = reinterpret_cast<const C*>(in) + (size_t)blockIdx.x * Y * M;
 #pragma unroll kSlabIoUnroll
-  for (int idx = tid; idx < Y * M; idx += kFftThreads) {
-    const int y = idx / M, j = idx % M;
-    tile[j * P + y] = in2[idx];
+    for (int idx = tid; idx < Y * M; idx += kFftThreads) {
+      const int y = idx / M, j = idx % M;
+      tile[j * P + y] = in2[idx];
+    }
+    __syncthreads();
+    real_fft_fwd<R, M, Y>(tile, P, 1, twM, twz, tid, kFftThreads);  // Z: half-length FFT + fused split
   }
-  __syncthreads();
-  real_fft_fwd<R, M, Y>(tile, P, 1, twM, twz, tid, kFftThreads);  // Z: half-length FFT + fused split
   __syncthreads();
   // Y transform; its last stage stores straight to the spectrum slab [ry][rz] (lanes over rz)
   GSide<C> gout{spec + (size_t)blockIdx.x * Y * ZC, ZC, ZC};
@@ -399,13 +420,18 @@ slab_inv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec,
   GSide<C> gin{const_cast<C*>(spec) + (size_t)blockIdx.x * Y * ZC, ZC, ZC};
   ColFFT<R, Y, Y, 0, ZC>::template inv_g<true, false>(tile, 1, P, twy, tid, kFftThreads, gin, gin);
   __syncthreads();
-  real_fft_inv<R, M, Y>(tile, P, 1, twM, twz, tid, kFftThreads);  // fused unsplit + inverse half-length FFT
-  __syncthreads();
-  C* o2 = reinterpret_cast<C*>(out) + (size_t)blockIdx.x * Y * M;
+  if constexpr (kZEdge<M, Y>) {
+    // fused unsplit stage, then the last radix stage stores straight to global memory (no drain loop)
+    real_fft_inv_g<R, M, Y>(out + (size_t)blockIdx.x * Y * Z, tile, P, twM, twz, tid, kFftThreads);
+  } else {
+    real_fft_inv<R, M, Y>(tile, P, 1, twM, twz, tid, kFftThreads);  // fused unsplit + inverse half-length FFT
+    __syncthreads();
+    C* o2 = reinterpret_cast<C*>(out) + (size_t)blockIdx.x * Y * M;
 #pragma unroll 4
-  for (int idx = tid; idx < Y * M; idx += kFftThreads) {
-    const int y = idx / M, j = idx % M;
-    o2[idx] = tile[j * P + y];
+    for (int idx = tid; idx < Y * M; idx += kFftThreads) {
+      const int y = idx / M, j = idx % M;
+      o2[idx] = tile[j * P + y];
+    }
   }
 }
 
@@ -489,15 +515,11 @@ cslab_fwd_kernel(float2* __restrict__ spec, const float* __restrict__ in, const 
   for (int j = tid; j < Z; j += kCsThreads) twz[j] = twz_g[j];
   for (int j = tid; j < M; j += kCsThreads) twM[j] = twz_g[2 * j];
   for (int j = tid; j < Y; j += kCsThreads) twy[j] = twy_g[j];
-  const float2* in2 = reinterpret_cast<const float2*>(in) + (slab * Y + rank * kCsYL) * M;
-#pragma unroll kSlabIoUnroll
-  for (int idx = tid; idx < kCsYL * M; idx += kCsThreads) {
-    const int yl = idx / M, j = idx % M;
-    tile[(j + (j >> 5)) * P + yl] = in2[idx];
-  }
+  float2* in2 = reinterpret_cast<float2*>(const_cast<float*>(in)) + (slab * Y + rank * kCsYL) * M;
   __syncthreads();
-  // Z: half-length complex FFT (16 x 8) with the real split fused into its last stage, on panel rows
-  fft_stage<float, M, M, 16, kCsYL, false, false, false, 5>(tile, P, 1, twM, tid, kCsThreads, GSide<float2>(), P);
+  // Z: half-length complex FFT (16 x 8) on panel rows; first stage straight from global memory, the
+  // real split fused into the last one
+  zedge_stage<float, M, 16, kCsYL, false, 5>(in2, tile, P, twM, tid, kCsThreads, P);
   __syncthreads();
   real_edge_stage<float, M, kCsYL, false, 5>(tile, P, 1, twz, tid, kCsThreads, P, kCsNyq);
   cg::this_cluster().sync();
@@ -534,14 +556,8 @@ cslab_inv_kernel(float* __restrict__ out, const float2* __restrict__ spec, const
   cg::this_cluster().sync();
   real_edge_stage<float, M, kCsYL, true, 5>(tile, P, 1, twz, tid, kCsThreads, P, kCsNyq);
   __syncthreads();
-  fft_stage<float, M, M, 16, kCsYL, true, false, false, 5>(tile, P, 1, twM, tid, kCsThreads, GSide<float2>(), P);
-  __syncthreads();
   float2* o2 = reinterpret_cast<float2*>(out) + (slab * Y + rank * kCsYL) * M;
-#pragma unroll 4
-  for (int idx = tid; idx < kCsYL * M; idx += kCsThreads) {
-    const int yl = idx / M, j = idx % M;
-    o2[idx] = tile[(j + (j >> 5)) * P + yl];
-  }
+  zedge_stage<float, M, 16, kCsYL, true, 5>(o2, tile, P, twM, tid, kCsThreads, P);
 }
 
 // Y pass (3-D only): in-place column FFT over the middle axis on [NY x T] tiles.
@@ -773,8 +789,7 @@ xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
       __syncthreads();
     }
     fft_stage_edge<R, NX, RAD0, T, true>(base, plane, tile, T, 1, tw, lvalid, tid, kFftThreads);
-    return;
-  }
+  } else {
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch)
     col_fft_fwd_from_global<R, NX, T>(base + (long long)ch * NX * plane, plane, tile + ch * NX * T, T, 1, tw,
@@ -823,6 +838,7 @@ xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
   for (int ch = 0; ch < NCH; ++ch)
     col_fft_inv_to_global<R, NX, T>(base + (long long)ch * NX * plane, plane, tile + ch * NX * T, T, 1, tw,
                                     lvalid, tid, kFftThreads);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

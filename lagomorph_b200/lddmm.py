@@ -242,13 +242,50 @@ def expmap(metric, m0, T=1.0, num_steps=10, phiinv=None, mommask=None, checkpoin
     return phiinv
 
 
-def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chunk=4):
+def _auto_chunks(N, cap=5):
+    """Chunk sizes for expmap_host: every chunk costs a fixed ~0.25 ms of launch tails, so chunks
+    should be few and large, but the first host->device copy and the last device->host copy are
+    exposed and a chunk's copy has to hide behind its neighbour's compute (a 128^3 subject copies in
+    about half the time it computes on PCIe 5 x16). So sizes ramp up from 1 by doubling, ramp down to
+    1 by thirds, and the middle is cut into chunks of `cap`: N = 16 -> [1, 2, 4, 5, 3, 1]."""
+    head, tail = [], []
+    h, t, left = 1, 1, N
+    while left > 0 and (h < cap or t < cap):
+        if h < cap:
+            k = min(h, left)
+            head.append(k)
+            left -= k
+            h *= 2
+        if left > 0 and t < cap:
+            k = min(t, left)
+            tail.insert(0, k)
+            left -= k
+            t *= 3
+    mid = []
+    if left > 0:
+        n = -(-left // cap)
+        base, extra = divmod(left, n)
+        mid = [base + (1 if i < extra else 0) for i in range(n)]
+    sizes = head + mid + tail
+    i = 1
+    while i < len(sizes) - 1:           # no stray single subject in the middle
+        if sizes[i] == 1:
+            j = i - 1 if sizes[i - 1] <= sizes[i + 1] else i + 1
+            sizes[j] += 1
+            del sizes[i]
+        else:
+            i += 1
+    return sizes
+
+
+def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chunk="auto"):
     """Shoot momenta that live in (pinned) HOST memory and return the deformations in host memory.
 
     Subjects are independent, so the batch is cut into chunks that flow through a three-stage
     pipeline on separate CUDA streams: host->device copy of chunk i+1, EPDiff shoot of chunk i,
-    device->host copy of chunk i-1 all overlap (PCIe is full duplex). Same result as
-    `expmap(metric, m0_host.cuda(), ...).cpu()`. No autograd.
+    device->host copy of chunk i-1 all overlap (PCIe is full duplex). (Shooting consecutive chunks
+    on alternating compute streams was measured: no gain, and erratic with the caching allocator.)
+    Same result as `expmap(metric, m0_host.cuda(), ...).cpu()`. No autograd.
     """
     if m0_host.is_cuda:
         raise RuntimeError("expmap_host takes host tensors; use expmap for device tensors")
@@ -258,12 +295,15 @@ def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chu
         out = torch.empty_like(m0_host, pin_memory=True)
     if N == 0:
         return out
-    # chunk: an int (uniform chunks) or a list of chunk sizes. With an int the first and last chunks
-    # are halved (down to 1 subject) because their copy cannot hide behind any compute.
-    if isinstance(chunk, (list, tuple)):
+    # chunk: "auto", an int (uniform chunks) or a list of chunk sizes.
+    if isinstance(chunk, str):
+        sizes = _auto_chunks(N)
+    elif isinstance(chunk, (list, tuple)):
         sizes = [int(c) for c in chunk if int(c) > 0]
         assert sum(sizes) == N, "chunk sizes must add up to the batch"
     else:
+        # uniform chunks; the first and last are halved (down to 1 subject) because their copy
+        # cannot hide behind any compute
         chunk = max(1, min(int(chunk), N))
         edge = max(1, chunk // 2)
         sizes = []

@@ -118,7 +118,10 @@ def test_fused_adjrep(lm, orc, dim, sh, dtype):
         assert relerr(lm.compose(phi.cuda(), v.cuda(), ds, dt), orc.compose(phi, v, ds, dt)) <= tol_for(dtype)
 
 
-FLUID_SHAPES = {2: [(3, 3), (6, 10), (16, 32), (64, 64)], 3: [(3, 3, 3), (4, 6, 5), (8, 16, 32), (32, 8, 16)]}
+# incl. shapes whose Z transform takes the global-memory edge stage (two radix stages: Z >= 64) in the
+# line kernels (Y != Z) and in the slab kernels (Y == Z)
+FLUID_SHAPES = {2: [(3, 3), (6, 10), (16, 32), (64, 64), (32, 128), (16, 256)],
+                3: [(3, 3, 3), (4, 6, 5), (8, 16, 32), (32, 8, 16), (16, 32, 64), (8, 64, 64), (8, 16, 128)]}
 FLUID_PARAMS = [[0.1, 0.0, 0.01], [0.1, 0.01, 0.001], [1.0, 0.1, 0.01]]
 
 
@@ -132,6 +135,16 @@ def test_fluid_metric(lm, orc, dim, dtype, params):
         tol = 1e-5 if dtype == torch.float32 else 1e-11
         assert l2err(gm.sharp(m.cuda()), om.sharp(m)) <= tol, (sh, "sharp")
         assert l2err(gm.flat(m.cuda()), om.flat(m)) <= tol, (sh, "flat")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fluid_metric_partial_line_block(lm, orc, dtype):
+    """fewer lines than one CTA of the Z pass holds (16 < 32): the padded fill path, not the edge stage"""
+    m = randn((1, 2, 8, 64), dtype, 62)
+    om, gm = orc.FluidMetric([0.1, 0.01, 0.001]), lm.FluidMetric([0.1, 0.01, 0.001])
+    tol = 1e-5 if dtype == torch.float32 else 1e-11
+    assert l2err(gm.sharp(m.cuda()), om.sharp(m)) <= tol
+    assert l2err(gm.flat(m.cuda()), om.flat(m)) <= tol
 
 
 @pytest.mark.parametrize("dim", [2, 3])
