@@ -211,7 +211,15 @@ def main():
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        # nvidia-smi delivers a sample every 100 ms and the timed region of the default run is
+        # shorter than that: keep the same workload running (untimed) until a few samples exist, so
+        # the reported clocks / throttle reasons are always "under this load"
+        t_tail = time.perf_counter()
+        while len(sampler.rows) < 4 and time.perf_counter() - t_tail < 3.0 and sampler.proc is not None:
+            h = shoot()
+            torch.cuda.synchronize()
         clocks = sampler.stop()
+        clocks["window"] = "warm-up + timed region + untimed tail of the same workload"
         launches = lm.launch_count() - n0
         t = torch.tensor([ms], device=dev)
         if world > 1:
@@ -282,14 +290,15 @@ def main():
         breakdown[k] = entry
     if dom is not None and "achieved_gbs" in breakdown[dom]:
         traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if args.workload == "c2" and os.path.exists(tpath):
+        tname = {"c2": "r1_traffic.json", "c3": "r1_traffic_c3.json"}.get(args.workload)
+        tpath = os.path.join(ROOT, "profiles", tname) if tname else None
+        if tpath and os.path.exists(tpath):
             t = json.load(open(tpath)).get(dom)
             if t:
                 traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
         roofline = {"bound": "hbm", "kernel": dom, "achieved": breakdown[dom]["achieved_gbs"], "peak": hbm,
                     "unit": "GB/s", "frac": breakdown[dom]["frac"], "traffic": traffic,
-                    "traffic_source": "profiles/r1_traffic.json (ncu --set full)" if traffic else None,
+                    "traffic_source": "profiles/%s (ncu --set full)" % tname if traffic else None,
                     "algorithmic_bytes_per_launch": breakdown[dom].get("alg_bytes_per_launch"),
                     "peak_source": peak_src, "algorithmic_bytes_per_voxel": alg_bytes(dom, shape)}
     step_frac = main_res["value"] / world * ALG_BYTES_PER_VOXEL_STEP / 1e9 / hbm

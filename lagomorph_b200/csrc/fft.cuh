@@ -167,6 +167,11 @@ __device__ __forceinline__ void fft_stage(typename Cx<R>::T* tile, int rs, int l
   constexpr int SUB = BLOCK / RAD;
   constexpr int ITEMS = L * (N / RAD);
   constexpr int BITS = ilog2(RAD);
+#ifndef LGM_GSRC_UNROLL
+#define LGM_GSRC_UNROLL 1
+#endif
+  constexpr int kUnroll = GSRC ? LGM_GSRC_UNROLL : 1;  // items whose global loads are in flight together
+#pragma unroll kUnroll
   for (int it = tid; it < ITEMS; it += nth) {
     const int l = it % L, q = it / L;
     const int blk = q / SUB, rest = q % SUB;
@@ -612,6 +617,11 @@ __device__ __forceinline__ void zedge_stage(typename Cx<R>::T* __restrict__ g, t
   constexpr int W = SUB < 32 ? 32 / SUB : 1;   // lines per warp
   constexpr int BITS = ilog2(RAD);
   static_assert(L % 32 == 0 && (SUB >= 32 || 32 % SUB == 0), "zedge_stage: L must be a multiple of 32");
+#ifndef LGM_ZEDGE_UNROLL
+#define LGM_ZEDGE_UNROLL 1
+#endif
+  constexpr int kUnroll = INV ? 1 : LGM_ZEDGE_UNROLL;  // forward: items whose global loads are in flight together
+#pragma unroll kUnroll
   for (int it = tid; it < L * SUB; it += nth) {
     const int rest = it % SUB, slot = it / SUB;
     const int l = (SUB < 32) ? (slot / 32) * 32 + (slot % W) * SUB + (slot % 32) / W : slot;

@@ -1033,16 +1033,21 @@ static int slab_launch(bool inv, void* real, typename Cx<R>::T* spec, long long 
 }
 // 256 x 256 slabs (fp32): four-CTA cluster kernels, see cslab_fwd_kernel.
 static int cslab_launch(bool inv, void* real, float2* spec, long long slabs, const FluidPlan& p, cudaStream_t s) {
-  static const bool off = getenv("LGM_NO_CLUSTER_SLAB") != nullptr;  // kernel experiments only
-  if (off) return LGM_EUNSUP;
+  // LGM_NO_CLUSTER_SLAB: kernel experiments. `broken` is set when the device refuses the cluster
+  // launch (e.g. a partition without enough co-schedulable SMs): the unfused passes take over.
+  static const bool off = getenv("LGM_NO_CLUSTER_SLAB") != nullptr;
+  static bool broken = false;
+  if (off || broken) return LGM_EUNSUP;
   const size_t smem = sizeof(float2) * ((size_t)kCsRows * kCsP + 256 + 128 + 256);
   if (!inv) {
-    LGM_CUDA_TRY(set_smem(cslab_fwd_kernel, smem), "cslab_fwd smem");
+    if (set_smem(cslab_fwd_kernel, smem) != cudaSuccess) { cudaGetLastError(); broken = true; return LGM_EUNSUP; }
     cslab_fwd_kernel<<<(unsigned)(kCsNC * slabs), kCsThreads, smem, s>>>(spec, (const float*)real, (const float2*)p.tw[2], (const float2*)p.tw[1]);
+    if (cudaPeekAtLastError() != cudaSuccess) { cudaGetLastError(); broken = true; return LGM_EUNSUP; }
     count_launch("slab_fwd", s);
   } else {
-    LGM_CUDA_TRY(set_smem(cslab_inv_kernel, smem), "cslab_inv smem");
+    if (set_smem(cslab_inv_kernel, smem) != cudaSuccess) { cudaGetLastError(); broken = true; return LGM_EUNSUP; }
     cslab_inv_kernel<<<(unsigned)(kCsNC * slabs), kCsThreads, smem, s>>>((float*)real, spec, (const float2*)p.tw[2], (const float2*)p.tw[1]);
+    if (cudaPeekAtLastError() != cudaSuccess) { cudaGetLastError(); broken = true; return LGM_EUNSUP; }
     count_launch("slab_inv", s);
   }
   return LGM_OK;
@@ -1128,12 +1133,17 @@ static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64
       LGM_SWITCH_POW2(X, MAXN, rc = (FL::template xpass<NN, 2>(spec, g, (long long)Zc, Zc, p, inverse, alpha, beta, gamma, scale, s)));
       if (rc) return rc;
     }
+    rc = LGM_EUNSUP;
     if (slab) {
       rc = slab_pass<R>(true, Y, nlast, (void*)out_g, spec, g * dim * X, p, s);
-    } else {
-      rc = LGM_EUNSUP;
-      LGM_SWITCH_Z(nlast, MAXN, rc = FL::template zinv<NN>(out_g, spec, rows, (const C*)p.tw[dim - 1], s));
+      if (rc == LGM_EUNSUP) {  // cluster launch refused after the forward slab ran: unfused inverse passes
+        LGM_SWITCH_POW2(Y, MAXN, rc = (FL::template ypass<NN, true>(spec, (int)(g * dim), X, Zc, (const C*)p.tw[1], s)));
+        if (rc) return rc;
+        rc = LGM_EUNSUP;
+      }
     }
+    if (rc == LGM_EUNSUP)
+      LGM_SWITCH_Z(nlast, MAXN, rc = FL::template zinv<NN>(out_g, spec, rows, (const C*)p.tw[dim - 1], s));
     if (rc) return rc;
   }
   return LGM_OK;

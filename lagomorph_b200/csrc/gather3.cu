@@ -18,6 +18,9 @@
 #ifndef LGM_ADSTAR_MINB
 #define LGM_ADSTAR_MINB 4  /* CTAs/SM the Ad_star instantiation is compiled for (64 registers) */
 #endif
+#ifndef LGM_COMPOSE_MINB
+#define LGM_COMPOSE_MINB 5
+#endif
 #ifndef LGM_GATHER_BX
 #define LGM_GATHER_BX 1  /* 2,4,8 measured equal on B200: the gathers are L1-data-pipe bound, not L2 bound */
 #endif
@@ -27,7 +30,7 @@ namespace lgm {
 // MODE 0: Ad_star (a = phiinv, b = m0); MODE 1: compose (a = u, b = v).
 // blockDim = (32, 8): a warp walks one z row (lane = z, NV chunks of 32), a CTA covers 8 y rows.
 template <int MODE, int NV, int BX>
-__global__ void __launch_bounds__(256, MODE == 0 ? LGM_ADSTAR_MINB : 5)
+__global__ void __launch_bounds__(256, MODE == 0 ? LGM_ADSTAR_MINB : LGM_COMPOSE_MINB)
 gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
                int X, int Y, int Z, float dh, float dl, float dsr, float dtr) {
   // blockDim = (32, 8/BX, BX): BX neighbouring x slabs share a CTA so that the upper-x corner rows

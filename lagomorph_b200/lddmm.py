@@ -242,34 +242,31 @@ def expmap(metric, m0, T=1.0, num_steps=10, phiinv=None, mommask=None, checkpoin
     return phiinv
 
 
-def _auto_chunks(N, cap=5):
-    """Chunk sizes for expmap_host: every chunk costs a fixed ~0.25 ms of launch tails, so chunks
-    should be few and large, but the first host->device copy and the last device->host copy are
-    exposed and a chunk's copy has to hide behind its neighbour's compute (a 128^3 subject copies in
-    about half the time it computes on PCIe 5 x16). So sizes ramp up from 1 by doubling, ramp down to
-    1 by thirds, and the middle is cut into chunks of `cap`: N = 16 -> [1, 2, 4, 5, 3, 1]."""
+def _auto_chunks(N, num_steps=10, cap=5):
+    """Chunk sizes for expmap_host. Every chunk costs a fixed ~0.25 ms of launch tails, so chunks
+    should be few and large; but the first host->device copy and the last device->host copy are
+    exposed, and a chunk's copy has to hide behind its neighbour's compute. With r = copy time /
+    compute time per subject (12 B per voxel over ~55 GB/s of PCIe 5 x16 against ~22 G voxel-steps/s:
+    r = 4.8 / num_steps) the sizes may grow by 1/r per chunk from 1 at the head, shrink to 1 at the
+    tail, and are capped in the middle: N = 16, 10 steps -> [1, 2, 4, 5, 3, 1]; 5 steps at any N
+    (copy as slow as compute) -> single subjects."""
+    g = max(1.0, num_steps / 4.8)
     head, tail = [], []
-    h, t, left = 1, 1, N
-    while left > 0 and (h < cap or t < cap):
-        if h < cap:
-            k = min(h, left)
-            head.append(k)
-            left -= k
-            h *= 2
-        if left > 0 and t < cap:
-            k = min(t, left)
+    h, t, left = 1.0, 1.0, N
+    while left > 0:
+        k = min(int(h), cap, left)
+        head.append(k)
+        left -= k
+        h *= g
+        if left > 0:
+            k = min(int(t), cap, left)
             tail.insert(0, k)
             left -= k
-            t *= 3
-    mid = []
-    if left > 0:
-        n = -(-left // cap)
-        base, extra = divmod(left, n)
-        mid = [base + (1 if i < extra else 0) for i in range(n)]
-    sizes = head + mid + tail
+            t *= 1.5 * g if g >= 1.5 else g
+    sizes = head + tail
     i = 1
-    while i < len(sizes) - 1:           # no stray single subject in the middle
-        if sizes[i] == 1:
+    while i < len(sizes) - 1:           # no stray single subject between larger chunks
+        if sizes[i] == 1 and sizes[i - 1] > 1 and sizes[i + 1] > 1:
             j = i - 1 if sizes[i - 1] <= sizes[i + 1] else i + 1
             sizes[j] += 1
             del sizes[i]
@@ -297,7 +294,7 @@ def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chu
         return out
     # chunk: "auto", an int (uniform chunks) or a list of chunk sizes.
     if isinstance(chunk, str):
-        sizes = _auto_chunks(N)
+        sizes = _auto_chunks(N, num_steps)
     elif isinstance(chunk, (list, tuple)):
         sizes = [int(c) for c in chunk if int(c) > 0]
         assert sum(sizes) == N, "chunk sizes must add up to the batch"
