@@ -507,9 +507,18 @@ extern "C" int lgm_jtvf_bwd(int dtype, void* d_v, void* d_w, const void* gout, c
   CHECK_N(N);
   DISPATCH_RD(dtype, dim, jtvf_bwd_t, d_v, d_w, gout, v, w, N, C, shape, displacement, transpose, (cudaStream_t)stream);
 }
+namespace lgm {  // fp32 3-D fast paths (stencil3.cu); LGM_EUNSUP = not applicable
+int ad_star3_f32(void* out, const void* v, const void* m, int64_t N, const int64_t* sh, cudaStream_t s);
+int jtvf_adj3_f32(void* out, const void* z, const void* w, int64_t N, const int64_t* sh, cudaStream_t s);
+}  // namespace lgm
+
 extern "C" int lgm_jtvf_adj_fwd(int dtype, void* out, const void* z, const void* w, int64_t N,
                                 int64_t C, int dim, const int64_t* shape, void* stream) {
   CHECK_N(N);
+  if (dtype == LGM_F32 && dim == 3 && C == 3 && N > 0) {
+    int rc = jtvf_adj3_f32(out, z, w, N, shape, (cudaStream_t)stream);
+    if (rc != LGM_EUNSUP) return rc;
+  }
   DISPATCH_RD(dtype, dim, jtvf_adj_fwd_t, out, z, w, N, C, shape, (cudaStream_t)stream);
 }
 extern "C" int lgm_jtvf_adj_bwd(int dtype, void* d_z, void* d_w, const void* gout, const void* z,
@@ -521,6 +530,10 @@ extern "C" int lgm_jtvf_adj_bwd(int dtype, void* d_z, void* d_w, const void* gou
 extern "C" int lgm_ad_star_fwd(int dtype, void* out, const void* v, const void* m, int64_t N,
                                int dim, const int64_t* shape, void* stream) {
   CHECK_N(N);
+  if (dtype == LGM_F32 && dim == 3 && N > 0) {
+    int rc = ad_star3_f32(out, v, m, N, shape, (cudaStream_t)stream);
+    if (rc != LGM_EUNSUP) return rc;
+  }
   DISPATCH_RD(dtype, dim, ad_star_t, out, v, m, N, shape, (cudaStream_t)stream);
 }
 extern "C" int lgm_ad_fwd(int dtype, void* out, const void* v, const void* w, int64_t N, int dim,

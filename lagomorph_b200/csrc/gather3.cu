@@ -18,6 +18,20 @@
 #ifndef LGM_ADSTAR_MINB
 #define LGM_ADSTAR_MINB 4  /* CTAs/SM the Ad_star instantiation is compiled for (64 registers) */
 #endif
+// cache hints (kernel experiments): 1 = streaming stores, 2 = + streaming centre loads
+#ifndef LGM_GATHER_HINTS
+#define LGM_GATHER_HINTS 0
+#endif
+#if LGM_GATHER_HINTS >= 1
+#define LGM_ST(p, v) __stcs((p), (v))
+#else
+#define LGM_ST(p, v) (*(p) = (v))
+#endif
+#if LGM_GATHER_HINTS >= 2
+#define LGM_LDC(p) __ldcs(p)
+#else
+#define LGM_LDC(p) __ldg(p)
+#endif
 #ifndef LGM_COMPOSE_MINB
 #define LGM_COMPOSE_MINB 5
 #endif
@@ -70,9 +84,9 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
   for (int v = 0; v < NV; ++v) {
     const int k = (blockIdx.x * NV + v) * 32 + threadIdx.x;
     if (k < Z) {
-      Apre[v][0] = __ldg(an + (row + k));  // literal addressing: must not wait for `four`
-      Apre[v][1] = __ldg(an1 + (row + k));
-      Apre[v][2] = __ldg(an2 + (row + k));
+      Apre[v][0] = LGM_LDC(an + (row + k));  // literal addressing: must not wait for `four`
+      Apre[v][1] = LGM_LDC(an1 + (row + k));
+      Apre[v][2] = LGM_LDC(an2 + (row + k));
     }
   }
 #pragma unroll
@@ -104,9 +118,9 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
     const float m1v = trilerp(bn1, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv, four);
     const float m2v = trilerp(bn2, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv, four);
     if (MODE == 1) {
-      *at4(on, c0, four) = __fadd_rn(__fmul_rn(dsr, A0), __fmul_rn(dtr, m0v));
-      *at4(on1, c0, four) = __fadd_rn(__fmul_rn(dsr, A1), __fmul_rn(dtr, m1v));
-      *at4(on2, c0, four) = __fadd_rn(__fmul_rn(dsr, A2), __fmul_rn(dtr, m2v));
+      LGM_ST(at4(on, c0, four), __fadd_rn(__fmul_rn(dsr, A0), __fmul_rn(dtr, m0v)));
+      LGM_ST(at4(on1, c0, four), __fadd_rn(__fmul_rn(dsr, A1), __fmul_rn(dtr, m1v)));
+      LGM_ST(at4(on2, c0, four), __fadd_rn(__fmul_rn(dsr, A2), __fmul_rn(dtr, m2v)));
     } else {
       const int ixp = c0 + xp, ixm = c0 + xm, iyp = c0 + yp, iym = c0 + ym;
       const int izp = c0 + ((k < Z - 1) ? 1 : 0), izm = c0 - ((k > 0) ? 1 : 0);
@@ -120,7 +134,7 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
         if (c == 0) g0 += 1.f;
         if (c == 1) g1 += 1.f;
         if (c == 2) g2 += 1.f;
-        *at4(oc[c], c0, four) = g0 * m0v + g1 * m1v + g2 * m2v;  // diff.cu:118-120
+        LGM_ST(at4(oc[c], c0, four), g0 * m0v + g1 * m1v + g2 * m2v);  // diff.cu:118-120
       }
     }
   }
@@ -128,10 +142,13 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
 
 // Plain interp (cuda/interp.cu:47-78), any channel count, optional broadcast image: same thread
 // mapping and corner-pair gather as above, weights computed once per voxel for all channels.
-template <int NV, bool UNIT_DT>
+// CC: compile-time channel count (0 = runtime C): the common C = 1 / C = 3 cases unroll the channel loop,
+// so all 8*C corner loads of a voxel are in flight together.
+template <int NV, bool UNIT_DT, int CC>
 __global__ void __launch_bounds__(256)
 interp3_kernel(float* __restrict__ out, const float* __restrict__ I, const float* __restrict__ u, int X,
-               int Y, int Z, int C, size_t I_batch_stride, float dh, float dl) {
+               int Y, int Z, int C_rt, size_t I_batch_stride, float dh, float dl) {
+  const int C = CC ? CC : C_rt;
   const int j = blockIdx.y * 8 + threadIdx.y;
   if (j >= Y) return;
   const int i = blockIdx.z % X;
@@ -171,20 +188,29 @@ interp3_kernel(float* __restrict__ out, const float* __restrict__ I, const float
     const unsigned ry0 = ay.i0 * sy, ry1 = ay.i1 * sy;
     const unsigned i00 = rx0 + ry0, i01 = rx0 + ry1, i10 = rx1 + ry0, i11 = rx1 + ry1;
     const float omt = 1.f - ax.t, omu = 1.f - ay.t, omv = 1.f - wv;
-    const float* Ic = In;
-    float* oc = on + c0;
-    for (int c = 0; c < C; ++c, Ic += V, oc += V)
-      *oc = trilerp(Ic, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv, four);
+    if constexpr (CC > 0) {
+      float r[CC];
+#pragma unroll
+      for (int c = 0; c < CC; ++c) r[c] = trilerp(In + c * V, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv, four);
+#pragma unroll
+      for (int c = 0; c < CC; ++c) on[c0 + c * V] = r[c];
+    } else {
+      const float* Ic = In;
+      float* oc = on + c0;
+      for (int c = 0; c < C; ++c, Ic += V, oc += V)
+        *oc = trilerp(Ic, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv, four);
+    }
   }
 }
 
 // d_u of interp (cuda/interp.cu:224-233): d_u[d] = sum_c (gout_c * dt) * d/dx_d I_c(h), with the
 // corner-difference gradient of include/interp.h:315-326. Same mapping / gathers as interp3_kernel.
-template <int NV, bool UNIT_DT>
+template <int NV, bool UNIT_DT, int CC>
 __global__ void __launch_bounds__(256)
 interp_du3_kernel(float* __restrict__ d_u, const float* __restrict__ go, const float* __restrict__ I,
-                  const float* __restrict__ u, int X, int Y, int Z, int C, size_t I_batch_stride, float dh,
+                  const float* __restrict__ u, int X, int Y, int Z, int C_rt, size_t I_batch_stride, float dh,
                   float dl, double dt) {
+  const int C = CC ? CC : C_rt;
   const int j = blockIdx.y * 8 + threadIdx.y;
   if (j >= Y) return;
   const int i = blockIdx.z % X;
@@ -225,6 +251,7 @@ interp_du3_kernel(float* __restrict__ d_u, const float* __restrict__ go, const f
     const float omt = 1.f - t, omu = 1.f - uu, omv = 1.f - w;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     const float* Ic = In;
+#pragma unroll
     for (int c = 0; c < C; ++c, Ic += V) {
       const float g = __ldg(gn + (size_t)c * V + c0);
       const float gd = (float)((double)g * dt);  // "diff *= dt" in double, cuda/interp.cu:230
@@ -250,10 +277,11 @@ interp_du3_kernel(float* __restrict__ d_u, const float* __restrict__ go, const f
 // is the lower-z corner of lane L+1: those two contributions are merged with one warp shuffle and
 // leave as ONE red.global.add, which halves the L2 atomic traffic (the limiter of this kernel).
 // Corner weights follow the reference's alternating "d = 1 - d" sequence (include/interp.h:437-453).
-template <int NV, bool UNIT_DT>
+template <int NV, bool UNIT_DT, int CC>
 __global__ void __launch_bounds__(256)
 splat3_kernel(float* __restrict__ d_I, const float* __restrict__ go, const float* __restrict__ u, int X,
-              int Y, int Z, int C, size_t I_batch_stride, float dh, float dl) {
+              int Y, int Z, int C_rt, size_t I_batch_stride, float dh, float dl) {
+  const int C = CC ? CC : C_rt;
   const int j = blockIdx.y * 8 + threadIdx.y;
   if (j >= Y) return;  // warp-uniform (a warp is one row)
   const int i = blockIdx.z % X;
@@ -302,6 +330,7 @@ splat3_kernel(float* __restrict__ d_I, const float* __restrict__ go, const float
       give[r] = (lane < 31) && (nxt == ahi) && (ahi != alo);
       took[r] = __shfl_up_sync(full, (int)give[r], 1) != 0 && lane > 0;
     }
+#pragma unroll
     for (int c = 0; c < C; ++c) {
       const float d = __ldg(gn + (size_t)c * V + c0);
       float* dc = dn + (size_t)c * V;
@@ -354,14 +383,16 @@ int interp3_f32(void* out, const void* I, const void* u, int64_t N, int64_t NI, 
   if (!fast3_ok(out, I, u, N, sh) || C < 1 || C > 0x7fffffff / (sh[0] * sh[1] * sh[2])) return LGM_EUNSUP;
   const size_t ibs = (NI < N) ? 0 : (size_t)C * sh[0] * sh[1] * sh[2];
   dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * sh[0])), block(32, 8);
+  const float dh = (dt == 1.0) ? 1.f : (float)dt, dl = (dt == 1.0) ? 0.f : (float)(dt - (double)dh);
+#define LGM_INTERP3(UNIT, CC)                                                                                   \
+  interp3_kernel<4, UNIT, CC><<<grid, block, 0, s>>>((float*)out, (const float*)I, (const float*)u, (int)sh[0], \
+                                                     (int)sh[1], (int)sh[2], (int)C, ibs, dh, dl)
   if (dt == 1.0) {
-    interp3_kernel<4, true><<<grid, block, 0, s>>>((float*)out, (const float*)I, (const float*)u, (int)sh[0],
-                                                   (int)sh[1], (int)sh[2], (int)C, ibs, 1.f, 0.f);
+    if (C == 1) LGM_INTERP3(true, 1); else if (C == 3) LGM_INTERP3(true, 3); else LGM_INTERP3(true, 0);
   } else {
-    const float dh = (float)dt, dl = (float)(dt - (double)dh);
-    interp3_kernel<4, false><<<grid, block, 0, s>>>((float*)out, (const float*)I, (const float*)u, (int)sh[0],
-                                                    (int)sh[1], (int)sh[2], (int)C, ibs, dh, dl);
+    if (C == 1) LGM_INTERP3(false, 1); else if (C == 3) LGM_INTERP3(false, 3); else LGM_INTERP3(false, 0);
   }
+#undef LGM_INTERP3
   count_launch("interp_fwd", s);
   return finish(s, "lgm_interp_fwd");
 }
@@ -373,14 +404,16 @@ int splat3_f32(void* d_I, const void* go, const void* u, int64_t N, int64_t NI, 
     return LGM_EUNSUP;
   const size_t ibs = (NI < N) ? 0 : (size_t)C * sh[0] * sh[1] * sh[2];
   dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * sh[0])), block(32, 8);
+  const float dh = (dt == 1.0) ? 1.f : (float)dt, dl = (dt == 1.0) ? 0.f : (float)(dt - (double)dh);
+#define LGM_SPLAT3(UNIT, CC)                                                                                    \
+  splat3_kernel<4, UNIT, CC><<<grid, block, 0, s>>>((float*)d_I, (const float*)go, (const float*)u, (int)sh[0], \
+                                                    (int)sh[1], (int)sh[2], (int)C, ibs, dh, dl)
   if (dt == 1.0) {
-    splat3_kernel<4, true><<<grid, block, 0, s>>>((float*)d_I, (const float*)go, (const float*)u, (int)sh[0],
-                                                  (int)sh[1], (int)sh[2], (int)C, ibs, 1.f, 0.f);
+    if (C == 1) LGM_SPLAT3(true, 1); else if (C == 3) LGM_SPLAT3(true, 3); else LGM_SPLAT3(true, 0);
   } else {
-    const float dh = (float)dt, dl = (float)(dt - (double)dh);
-    splat3_kernel<4, false><<<grid, block, 0, s>>>((float*)d_I, (const float*)go, (const float*)u, (int)sh[0],
-                                                   (int)sh[1], (int)sh[2], (int)C, ibs, dh, dl);
+    if (C == 1) LGM_SPLAT3(false, 1); else if (C == 3) LGM_SPLAT3(false, 3); else LGM_SPLAT3(false, 0);
   }
+#undef LGM_SPLAT3
   count_launch("interp_splat", s);
   return finish(s, "lgm_interp_bwd");
 }
@@ -390,14 +423,16 @@ int interp_du3_f32(void* d_u, const void* go, const void* I, const void* u, int6
   if (!fast3_ok(d_u, go, u, N, sh) || C < 1 || C > 0x7fffffff / (sh[0] * sh[1] * sh[2])) return LGM_EUNSUP;
   const size_t ibs = (NI < N) ? 0 : (size_t)C * sh[0] * sh[1] * sh[2];
   dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * sh[0])), block(32, 8);
+  const float dh = (dt == 1.0) ? 1.f : (float)dt, dl = (dt == 1.0) ? 0.f : (float)(dt - (double)dh);
+#define LGM_DU3(UNIT, CC)                                                                                                 \
+  interp_du3_kernel<4, UNIT, CC><<<grid, block, 0, s>>>((float*)d_u, (const float*)go, (const float*)I, (const float*)u, \
+                                                        (int)sh[0], (int)sh[1], (int)sh[2], (int)C, ibs, dh, dl, dt)
   if (dt == 1.0) {
-    interp_du3_kernel<4, true><<<grid, block, 0, s>>>((float*)d_u, (const float*)go, (const float*)I, (const float*)u,
-                                                      (int)sh[0], (int)sh[1], (int)sh[2], (int)C, ibs, 1.f, 0.f, dt);
+    if (C == 1) LGM_DU3(true, 1); else if (C == 3) LGM_DU3(true, 3); else LGM_DU3(true, 0);
   } else {
-    const float dh = (float)dt, dl = (float)(dt - (double)dh);
-    interp_du3_kernel<4, false><<<grid, block, 0, s>>>((float*)d_u, (const float*)go, (const float*)I, (const float*)u,
-                                                       (int)sh[0], (int)sh[1], (int)sh[2], (int)C, ibs, dh, dl, dt);
+    if (C == 1) LGM_DU3(false, 1); else if (C == 3) LGM_DU3(false, 3); else LGM_DU3(false, 0);
   }
+#undef LGM_DU3
   count_launch("interp_du", s);
   return finish(s, "lgm_interp_bwd");
 }
