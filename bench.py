@@ -52,6 +52,30 @@ def make_momenta(N, shape, seed, device=None, scale_to=4.0):
     return m
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers
+    are allocated (first touch places them on that node): with 8 ranks copying at once the
+    host<->device path, not the GPU, bounds the e2e number. Best effort: returns the node or None."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi SM clocks / throttle reasons sampled DURING the timed region."""
 
@@ -175,6 +199,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1
@@ -327,7 +352,8 @@ def main():
             "config": {"workload": args.workload, "shape": list(shape), "batch_per_gpu": batch,
                        "epdiff_steps": nsteps, "metric_params": PARAMS,
                        "l2": "inputs larger than L2 (%d MiB per field vs 126 MB)" % (batch * 3 * V * 4 >> 20),
-                       "parallelism": "subjects sharded over ranks, no data-path collective"},
+                       "parallelism": "subjects sharded over ranks, no data-path collective",
+                       "host_numa_node": numa},
             "hbm_roofline_frac_96B": step_frac,
             "roofline": roofline, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
             "e2e": main_res.get("e2e"), "gpu_launches": main_res["launches"], "clocks": main_res["clocks"],

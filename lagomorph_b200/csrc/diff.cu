@@ -495,6 +495,11 @@ using namespace lgm;
   LGM_REQUIRE((dim == 2 && geom_fits<2>(shape)) || (dim == 3 && geom_fits<3>(shape)),                  \
               "Only two- and three-dimensional fields of fewer than 2^31 voxels are supported")
 
+namespace lgm {  // fp32 3-D fast paths (stencil3.cu); LGM_EUNSUP = not applicable
+int ad_star3_f32(void* out, const void* v, const void* m, int64_t N, const int64_t* sh, cudaStream_t s);
+int jtvf_adj3_f32(void* out, const void* z, const void* w, int64_t N, const int64_t* sh, cudaStream_t s);
+}  // namespace lgm
+
 extern "C" int lgm_jtvf_fwd(int dtype, void* out, const void* v, const void* w, int64_t N,
                             int64_t C, int dim, const int64_t* shape, int displacement,
                             int transpose, void* stream) {
@@ -505,13 +510,24 @@ extern "C" int lgm_jtvf_bwd(int dtype, void* d_v, void* d_w, const void* gout, c
                             const void* w, int64_t N, int64_t C, int dim, const int64_t* shape,
                             int displacement, int transpose, void* stream) {
   CHECK_N(N);
+  if (dtype == LGM_F32 && dim == 3 && C == 3 && N > 0 && !thin<3>(shape)) {
+    // fp32 3-D vector fields: both gradients are operators that have tuned kernels of their own
+    //   d_w = jtvf(v, gout, displacement, !transpose)                  (diff.cu:311-335, :417-431)
+    //   d_v = sum_d D_d^T (w_d gout_c)  resp.  sum_d D_d^T (gout_d w_c)  (diff.cu:432-460, :336-407)
+    // (same arithmetic and accumulation order as jtvf_bwd_kernel, about half its time)
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = LGM_OK;
+    if (d_v) {
+      rc = transpose ? jtvf_adj3_f32(d_v, w, gout, N, shape, s) : jtvf_adj3_f32(d_v, gout, w, N, shape, s);
+      if (rc == LGM_EUNSUP) goto generic;
+      if (rc) return rc;
+    }
+    if (d_w) rc = jtvf_fwd_t<float, 3>(d_w, v, gout, N, C, shape, displacement, !transpose, s);
+    return rc;
+  }
+generic:
   DISPATCH_RD(dtype, dim, jtvf_bwd_t, d_v, d_w, gout, v, w, N, C, shape, displacement, transpose, (cudaStream_t)stream);
 }
-namespace lgm {  // fp32 3-D fast paths (stencil3.cu); LGM_EUNSUP = not applicable
-int ad_star3_f32(void* out, const void* v, const void* m, int64_t N, const int64_t* sh, cudaStream_t s);
-int jtvf_adj3_f32(void* out, const void* z, const void* w, int64_t N, const int64_t* sh, cudaStream_t s);
-}  // namespace lgm
-
 extern "C" int lgm_jtvf_adj_fwd(int dtype, void* out, const void* z, const void* w, int64_t N,
                                 int64_t C, int dim, const int64_t* shape, void* stream) {
   CHECK_N(N);

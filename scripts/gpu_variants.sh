@@ -1,7 +1,4 @@
-(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) | tee gpurun_out/pytest_gpu.log
-python bench_ops.py > gpurun_out/ops.json 2> gpurun_out/ops.err
-python -c "
-import json
-d=json.load(open('gpurun_out/ops.json'))
-for k,v in d['ops'].items(): print('%-45s %.4f ms  %.3f' % (k, v['ms'], v['frac_of_hbm_peak']))
-"
+for v in "" oldfluid; do
+  if [ -n "$v" ]; then export LGM_LIB_PATH=$PWD/lagomorph_b200/variants/lib_$v.so; else unset LGM_LIB_PATH; fi
+  python scripts/sharp_bench.py 16 128; python scripts/sharp_bench.py 4 256
+done 2>&1 | grep -v Warning | tee gpurun_out/variants.log
