@@ -74,6 +74,27 @@ def main():
     vg, wg = v.clone().requires_grad_(True), w.clone().requires_grad_(True)
     out2 = lm.jacobian_times_vectorfield(vg, wg)
     rec("jtvf backward (d_v + d_w)", timeit(lambda: torch.autograd.grad(out2, [vg, wg], go3, retain_graph=True)), 60)
+    del out, out2, ug, Ig, vg, wg
+    torch.cuda.empty_cache()
+    # BASELINE config 4: affine_interp at 192^3, batch 32 (forward 8 B/voxel; backward reads gout and I,
+    # splats d_I: 16 B/voxel + the d_A / d_T reductions)
+    N4, n4 = int(os.environ.get("OPS_N4", 32)), int(os.environ.get("OPS_SIZE4", 192))
+    V4 = n4 ** 3
+    I4 = torch.randn(N4, 1, n4, n4, n4, device=dev, generator=g)
+    A4 = torch.eye(3, device=dev).repeat(N4, 1, 1) + 0.05 * torch.randn(N4, 3, 3, device=dev, generator=g)
+    T4 = 2.0 * torch.randn(N4, 3, device=dev, generator=g)
+    go4 = torch.randn(N4, 1, n4, n4, n4, device=dev, generator=g)
+
+    def rec4(name, ms, bpv):
+        gbs = bpv * N4 * V4 / (ms * 1e-3) / 1e9
+        res[name] = {"ms": round(ms, 4), "alg_B_per_voxel": bpv, "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 3),
+                     "size": [N4, 1, n4, n4, n4]}
+    with torch.no_grad():
+        rec4("affine_interp forward (C4)", timeit(lambda: lm.affine_interp(I4, A4, T4)), 8)
+    Ig4, Ag4, Tg4 = I4.clone().requires_grad_(True), A4.clone().requires_grad_(True), T4.clone().requires_grad_(True)
+    out4 = lm.affine_interp(Ig4, Ag4, Tg4)
+    rec4("affine_interp backward (d_I + d_A + d_T) (C4)",
+         timeit(lambda: torch.autograd.grad(out4, [Ig4, Ag4, Tg4], go4, retain_graph=True)), 16)
     print(json.dumps({"N": N, "size": n, "hbm_peak_gbs": peak, "ops": res}))
 
 

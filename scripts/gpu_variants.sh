@@ -1,4 +1,4 @@
-for v in "" oldfluid; do
-  if [ -n "$v" ]; then export LGM_LIB_PATH=$PWD/lagomorph_b200/variants/lib_$v.so; else unset LGM_LIB_PATH; fi
-  python scripts/sharp_bench.py 16 128; python scripts/sharp_bench.py 4 256
-done 2>&1 | grep -v Warning | tee gpurun_out/variants.log
+python scripts/variant_bench.py c2 2>&1 | grep -v Warning | tee gpurun_out/variants.log
+LGM_NO_COMPOSE_MARCH=1 python scripts/variant_bench.py c2 2>&1 | grep -v Warning | tee -a gpurun_out/variants.log
+python scripts/variant_bench.py c3 2>&1 | grep -v Warning | tee -a gpurun_out/variants.log
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) | tee gpurun_out/pytest_gpu.log
