@@ -275,13 +275,14 @@ def _auto_chunks(N, num_steps=10, cap=5):
     return sizes
 
 
-def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chunk="auto"):
+def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chunk="auto", graphs=True):
     """Shoot momenta that live in (pinned) HOST memory and return the deformations in host memory.
 
     Subjects are independent, so the batch is cut into chunks that flow through a three-stage
     pipeline on separate CUDA streams: host->device copy of chunk i+1, EPDiff shoot of chunk i,
     device->host copy of chunk i-1 all overlap (PCIe is full duplex). (Shooting consecutive chunks
     on alternating compute streams was measured: no gain, and erratic with the caching allocator.)
+    With graphs=True (default) every chunk's shoot is replayed as a cached CUDA graph (_host_plan).
     Same result as `expmap(metric, m0_host.cuda(), ...).cpu()`. No autograd.
     """
     if m0_host.is_cuda:
@@ -322,7 +323,11 @@ def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chu
     s_in.wait_stream(cur)
     s_out.wait_stream(cur)
     nbuf = 3
-    dbuf = [torch.empty((maxc,) + tuple(m0_host.shape[1:]), dtype=m0_host.dtype, device=dev) for _ in range(nbuf)]
+    plan = _host_plan(metric, m0_host, T, num_steps, dev, sizes, nbuf) if graphs else None
+    if plan is not None:
+        dbuf = plan["dbuf"]
+    else:
+        dbuf = [torch.empty((maxc,) + tuple(m0_host.shape[1:]), dtype=m0_host.dtype, device=dev) for _ in range(nbuf)]
     in_done = [torch.cuda.Event() for _ in range(nbuf)]
     comp_done = [None] * nbuf  # input buffer of slot b has been consumed
     starts = [sum(sizes[:i]) for i in range(len(sizes))]
@@ -343,15 +348,63 @@ def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chu
         if ci + 1 < len(starts):
             issue_h2d(ci + 1)
         cur.wait_event(in_done[b])
-        with torch.no_grad():
-            h = expmap(metric, dbuf[b][:n], T=T, num_steps=num_steps)
+        if plan is not None:
+            plan["graphs"][ci].replay()      # the chunk's num_steps x 5 launches as one CUDA graph
+            h = plan["outs"][ci]
+        else:
+            with torch.no_grad():
+                h = expmap(metric, dbuf[b][:n], T=T, num_steps=num_steps)
         ev = torch.cuda.Event()
         ev.record(cur)
         comp_done[b] = ev
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev)
             out[st:st + n].copy_(h, non_blocking=True)
-            h.record_stream(s_out)
+            if plan is None:
+                h.record_stream(s_out)
     cur.wait_stream(s_out)
     cur.wait_stream(s_in)
     return out
+
+
+_HOST_PLANS = {}   # key -> plan; at most _HOST_PLANS_MAX entries (each holds its chunks' device buffers)
+_HOST_PLANS_MAX = 2
+
+
+def _host_plan(metric, m0_host, T, num_steps, dev, sizes, nbuf):
+    """CUDA graphs of the chunk shoots of expmap_host, cached per (device, shape, dtype, steps, metric,
+    chunk schedule). A chunk of one or two subjects is fifty short launches: replayed as a graph they
+    run back to back without launch gaps and without the Python / ctypes work per step. The plan owns
+    the staging buffers the graphs read and the deformation buffers they write. Returns None (eager
+    path) when capture is not possible."""
+    if os.environ.get("LGM_HOST_GRAPHS", "1") == "0" or not isinstance(metric, FluidMetric):
+        return None
+    if torch.cuda.is_current_stream_capturing():
+        return None
+    key = (dev.index, tuple(m0_host.shape[1:]), m0_host.dtype, int(num_steps), float(T),
+           tuple(float(p) for p in metric.params), tuple(sizes), nbuf)
+    plan = _HOST_PLANS.get(key)
+    if plan is not None:
+        return plan
+    try:
+        maxc = max(sizes)
+        dbuf = [torch.zeros((maxc,) + tuple(m0_host.shape[1:]), dtype=m0_host.dtype, device=dev) for _ in range(nbuf)]
+        with torch.no_grad():
+            expmap(metric, dbuf[0][:1], T=T, num_steps=1)   # builds the FFT tables outside any capture
+        torch.cuda.synchronize(dev)
+        graphs, outs = [], []
+        for ci, n in enumerate(sizes):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g), torch.no_grad():
+                h = expmap(metric, dbuf[ci % nbuf][:n], T=T, num_steps=num_steps)
+            graphs.append(g)
+            outs.append(h)
+        torch.cuda.synchronize(dev)
+        plan = {"dbuf": dbuf, "graphs": graphs, "outs": outs}
+    except Exception:
+        torch.cuda.synchronize(dev)
+        return None
+    while len(_HOST_PLANS) >= _HOST_PLANS_MAX:
+        _HOST_PLANS.pop(next(iter(_HOST_PLANS)))
+    _HOST_PLANS[key] = plan
+    return plan

@@ -26,12 +26,11 @@ for n in (1, 2, 3, 4, 8, 16):
 out = torch.empty_like(m_host).pin_memory()
 ms = t(lambda: m0.copy_(m_host, non_blocking=True)); print("H2D 384 MiB: %.2f ms = %.1f GB/s" % (ms, 0.4027 / ms * 1e3))
 ms = t(lambda: out.copy_(m0, non_blocking=True)); print("D2H 384 MiB: %.2f ms = %.1f GB/s" % (ms, 0.4027 / ms * 1e3))
-cfgs = [("auto", 1), ("auto", 2), (3, 1), ([1, 2, 4, 5, 3, 1], 1), ([1, 3, 5, 4, 2, 1], 1), ([2, 5, 5, 3, 1], 1),
-        ([1, 2, 4, 6, 2, 1], 1), ([1, 2, 3, 3, 3, 2, 1, 1], 1), ([1, 2, 4, 5, 3, 1], 2)]
+cfgs = [("auto", True), ("auto", False), (3, True), ([1, 2, 4, 6, 2, 1], True), ([2, 5, 6, 2, 1], True), ([1, 3, 6, 5, 1], True)]
 res = {i: [] for i in range(len(cfgs))}
 for rep in range(3):
-    for i, (chunk, ns) in enumerate(cfgs):
-        res[i].append(t(lambda: lm.expmap_host(metric, m_host, num_steps=nsteps, out=out, device=dev, chunk=chunk, streams=ns)))
-for i, (chunk, ns) in enumerate(cfgs):
+    for i, (chunk, gr) in enumerate(cfgs):
+        res[i].append(t(lambda: lm.expmap_host(metric, m_host, num_steps=nsteps, out=out, device=dev, chunk=chunk, graphs=gr)))
+for i, (chunk, gr) in enumerate(cfgs):
     ms = sorted(res[i])[1]
-    print("expmap_host chunk=%s streams=%d: %s ms  median %.2f G" % (chunk, ns, ["%.2f" % x for x in res[i]], 16 * V * nsteps / ms / 1e6))
+    print("expmap_host chunk=%s graphs=%s: %s ms  median %.2f G" % (chunk, gr, ["%.2f" % x for x in res[i]], 16 * V * nsteps / ms / 1e6))

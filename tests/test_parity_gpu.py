@@ -253,9 +253,21 @@ def test_expmap_host_pipeline(lm, orc):
     m0 = smooth_field((5, 3, 16, 16, 16), torch.float32, 72, amp=1.0, sigma=2.0)
     m0 = (m0 * (3.0 / orc.FluidMetric(params).sharp(m0).abs().max())).pin_memory()
     ref = lm.expmap(gm, m0.cuda(), num_steps=3).cpu()
-    out = lm.expmap_host(gm, m0, num_steps=3, chunk=2)
+    out = lm.expmap_host(gm, m0, num_steps=3, chunk=2, graphs=False)
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
+    # the cached CUDA-graph plan: first call captures, later calls replay on new data
+    for chunk in (2, "auto"):
+        out = lm.expmap_host(gm, m0, num_steps=3, chunk=chunk)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+    m1 = (m0 * 0.5).pin_memory()
+    ref1 = lm.expmap(gm, m1.cuda(), num_steps=3).cpu()
+    out1 = lm.expmap_host(gm, m1, num_steps=3, chunk="auto")
+    torch.cuda.synchronize()
+    assert torch.equal(out1, ref1)
+    from lagomorph_b200 import lddmm
+    assert len(lddmm._HOST_PLANS) >= 1, "expmap_host fell back to the eager path"
 
 
 @pytest.mark.parametrize("dim,sh", [(2, (16, 16)), (3, (8, 16, 16))])
