@@ -26,7 +26,8 @@ for n in (1, 2, 3, 4, 8, 16):
 out = torch.empty_like(m_host).pin_memory()
 ms = t(lambda: m0.copy_(m_host, non_blocking=True)); print("H2D 384 MiB: %.2f ms = %.1f GB/s" % (ms, 0.4027 / ms * 1e3))
 ms = t(lambda: out.copy_(m0, non_blocking=True)); print("D2H 384 MiB: %.2f ms = %.1f GB/s" % (ms, 0.4027 / ms * 1e3))
-cfgs = [("auto", True), ("auto", False), (3, True), ([1, 2, 4, 6, 2, 1], True), ([2, 5, 6, 2, 1], True), ([1, 3, 6, 5, 1], True)]
+cfgs = [("auto", True), (2, True), ([1, 2, 3, 3, 3, 2, 1, 1], True), ([1, 2, 3, 4, 3, 2, 1], True), ([1, 1, 2, 3, 3, 3, 2, 1], True),
+        ([1, 2, 4, 4, 3, 1, 1], True), ([1, 2, 4, 5, 2, 1, 1], True)]
 res = {i: [] for i in range(len(cfgs))}
 for rep in range(3):
     for i, (chunk, gr) in enumerate(cfgs):
