@@ -63,8 +63,16 @@ extern "C" int lgm_epdiff_step_fwd(int dtype, void* phiinv_out, const void* phii
     const char* phi_g = (const char*)phiinv + n0 * sub;
     const char* m0_g = (const char*)m0 + n0 * sub;
     char* out_g = (char*)phiinv_out + n0 * sub;
+    // alternate the traversal direction from kernel to kernel (rev_hint, common.cuh): Ad_star and compose
+    // run in direction p, the slab passes of sharp in !p (its X pass in p again); p flips every step
+    // because compose(p) leaves the far end of phiinv in L2 for the next step's Ad_star.
+    static thread_local int parity = 0;
+    static const bool alternate = getenv("LGM_NO_ALTERNATE") == nullptr;
+    const int p = alternate ? parity : 0;
+    if (n0 + G >= N) parity ^= 1;
+    rev_hint() = p;
     int rc = lgm_Ad_star_fwd(dtype, m, phi_g, m0_g, g, dim, shape, stream);
-    if (rc) return rc;
+    if (rc) { rev_hint() = 0; return rc; }
     if (mommask) {  // full-shape mask (N,dim,...), applied like `m = m * mommask` (lddmm.py:41-42)
       const long long total = g * dim * V;
       const char* mk = (const char*)mommask + n0 * sub;
@@ -74,10 +82,12 @@ extern "C" int lgm_epdiff_step_fwd(int dtype, void* phiinv_out, const void* phii
         mul_mask_kernel<double><<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((double*)m, (const double*)mk, total, total);
       count_launch("mul_mask", (cudaStream_t)stream);
     }
+    rev_hint() = alternate ? !p : 0;
     rc = lgm_fluid_apply(dtype, m, m, g, dim, shape, 1, alpha, beta, gamma, ws, scratch_bytes - (int64_t)field, stream);
-    if (rc) return rc;
+    rev_hint() = p;
     // compose_disp_vel(phiinv, v, -dt) = compose(v, phiinv, ds=-dt, dt=1)  (deform.py:58-62)
-    rc = lgm_compose_fwd(dtype, out_g, m, phi_g, g, dim, shape, -dt, 1.0, stream);
+    if (!rc) rc = lgm_compose_fwd(dtype, out_g, m, phi_g, g, dim, shape, -dt, 1.0, stream);
+    rev_hint() = 0;
     if (rc) return rc;
   }
   return LGM_OK;

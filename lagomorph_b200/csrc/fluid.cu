@@ -367,7 +367,8 @@ zinv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec, lon
 template <typename R, int Y, int Z>
 __global__ void __launch_bounds__(kFftThreads)
 slab_fwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in,
-                const typename Cx<R>::T* __restrict__ twz_g, const typename Cx<R>::T* __restrict__ twy_g) {
+                const typename Cx<R>::T* __restrict__ twz_g, const typename Cx<R>::T* __restrict__ twy_g, int rev) {
+  const unsigned bx = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   using C = typename Cx<R>::T;
   constexpr int M = Z / 2, P = Y + 1, ZC = M + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -382,9 +383,9 @@ slab_fwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in,
   if constexpr (kZEdge<M, Y>) {
     // Z: first radix stage straight from global memory (no fill loop), then the fused split stage
     __syncthreads();
-    real_fft_fwd_g<R, M, Y>(in + (size_t)blockIdx.x * Y * Z, tile, P, twM, twz, tid, kFftThreads);
+    real_fft_fwd_g<R, M, Y>(in + (size_t)bx * Y * Z, tile, P, twM, twz, tid, kFftThreads);
   } else {
-    const C* in2 = reinterpret_cast<const C*>(in) + (size_t)blockIdx.x * Y * M;
+    const C* in2 = reinterpret_cast<const C*>(in) + (size_t)bx * Y * M;
 #pragma unroll kSlabIoUnroll
     for (int idx = tid; idx < Y * M; idx += kFftThreads) {
       const int y = idx / M, j = idx % M;
@@ -395,7 +396,7 @@ slab_fwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in,
   }
   __syncthreads();
   // Y transform; its last stage stores straight to the spectrum slab [ry][rz] (lanes over rz)
-  GSide<C> gout{spec + (size_t)blockIdx.x * Y * ZC, ZC, ZC};
+  GSide<C> gout{spec + (size_t)bx * Y * ZC, ZC, ZC};
   ColFFT<R, Y, Y, 0, ZC>::template fwd_g<false, true>(tile, 1, P, twy, tid, kFftThreads, gout, gout);
 }
 
@@ -403,7 +404,8 @@ slab_fwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in,
 template <typename R, int Y, int Z>
 __global__ void __launch_bounds__(kFftThreads)
 slab_inv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec,
-                const typename Cx<R>::T* __restrict__ twz_g, const typename Cx<R>::T* __restrict__ twy_g) {
+                const typename Cx<R>::T* __restrict__ twz_g, const typename Cx<R>::T* __restrict__ twy_g, int rev) {
+  const unsigned bx = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   using C = typename Cx<R>::T;
   constexpr int M = Z / 2, P = Y + 1, ZC = M + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -417,16 +419,16 @@ slab_inv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec,
   for (int j = tid; j < Y; j += kFftThreads) twy[j] = twy_g[j];
   __syncthreads();
   // inverse Y transform; its first stage loads straight from the spectrum slab [ry][rz]
-  GSide<C> gin{const_cast<C*>(spec) + (size_t)blockIdx.x * Y * ZC, ZC, ZC};
+  GSide<C> gin{const_cast<C*>(spec) + (size_t)bx * Y * ZC, ZC, ZC};
   ColFFT<R, Y, Y, 0, ZC>::template inv_g<true, false>(tile, 1, P, twy, tid, kFftThreads, gin, gin);
   __syncthreads();
   if constexpr (kZEdge<M, Y>) {
     // fused unsplit stage, then the last radix stage stores straight to global memory (no drain loop)
-    real_fft_inv_g<R, M, Y>(out + (size_t)blockIdx.x * Y * Z, tile, P, twM, twz, tid, kFftThreads);
+    real_fft_inv_g<R, M, Y>(out + (size_t)bx * Y * Z, tile, P, twM, twz, tid, kFftThreads);
   } else {
     real_fft_inv<R, M, Y>(tile, P, 1, twM, twz, tid, kFftThreads);  // fused unsplit + inverse half-length FFT
     __syncthreads();
-    C* o2 = reinterpret_cast<C*>(out) + (size_t)blockIdx.x * Y * M;
+    C* o2 = reinterpret_cast<C*>(out) + (size_t)bx * Y * M;
 #pragma unroll 4
     for (int idx = tid; idx < Y * M; idx += kFftThreads) {
       const int y = idx / M, j = idx % M;
@@ -501,7 +503,7 @@ __device__ __forceinline__ void cslab_ypass(float2* tile, const float2* twy, int
 
 __global__ void __cluster_dims__(kCsNC, 1, 1) __launch_bounds__(kCsThreads, 3)
 cslab_fwd_kernel(float2* __restrict__ spec, const float* __restrict__ in, const float2* __restrict__ twz_g,
-                 const float2* __restrict__ twy_g) {
+                 const float2* __restrict__ twy_g, int rev) {
   namespace cg = cooperative_groups;
   constexpr int Y = 256, Z = 256, M = Z / 2, ZC = M + 1, P = kCsP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -511,7 +513,7 @@ cslab_fwd_kernel(float2* __restrict__ spec, const float* __restrict__ in, const 
   float2* twy = twM + M;                               // Y entries
   const int tid = threadIdx.x;
   const unsigned rank = cg::this_cluster().block_rank();
-  const size_t slab = blockIdx.x / kCsNC;
+  const size_t slab = rev ? (gridDim.x - 1 - blockIdx.x) / kCsNC : blockIdx.x / kCsNC;
   for (int j = tid; j < Z; j += kCsThreads) twz[j] = twz_g[j];
   for (int j = tid; j < M; j += kCsThreads) twM[j] = twz_g[2 * j];
   for (int j = tid; j < Y; j += kCsThreads) twy[j] = twy_g[j];
@@ -533,7 +535,7 @@ cslab_fwd_kernel(float2* __restrict__ spec, const float* __restrict__ in, const 
 
 __global__ void __cluster_dims__(kCsNC, 1, 1) __launch_bounds__(kCsThreads, 3)
 cslab_inv_kernel(float* __restrict__ out, const float2* __restrict__ spec, const float2* __restrict__ twz_g,
-                 const float2* __restrict__ twy_g) {
+                 const float2* __restrict__ twy_g, int rev) {
   namespace cg = cooperative_groups;
   constexpr int Y = 256, Z = 256, M = Z / 2, ZC = M + 1, P = kCsP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -543,7 +545,7 @@ cslab_inv_kernel(float* __restrict__ out, const float2* __restrict__ spec, const
   float2* twy = twM + M;
   const int tid = threadIdx.x;
   const unsigned rank = cg::this_cluster().block_rank();
-  const size_t slab = blockIdx.x / kCsNC;
+  const size_t slab = rev ? (gridDim.x - 1 - blockIdx.x) / kCsNC : blockIdx.x / kCsNC;
   for (int j = tid; j < Z; j += kCsThreads) twz[j] = twz_g[j];
   for (int j = tid; j < M; j += kCsThreads) twM[j] = twz_g[2 * j];
   for (int j = tid; j < Y; j += kCsThreads) twy[j] = twy_g[j];
@@ -724,9 +726,11 @@ xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
               const typename Cx<R>::T* __restrict__ tw_g, const R* __restrict__ wl0,
               const R* __restrict__ sl0, const R* __restrict__ wl1, const R* __restrict__ sl1,
               const R* __restrict__ wl2, const R* __restrict__ sl2, double alpha, double beta,
-              double gamma, R scale) {
+              double gamma, R scale, int rev) {
   using C = typename Cx<R>::T;
   static_assert(kFftThreads % T == 0, "a thread must own one column");
+  const unsigned bx = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const unsigned by = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C* tile = reinterpret_cast<C*>(smem_raw);  // NCH x NX x T
   C* tw = tile + NCH * NX * T;
@@ -737,9 +741,9 @@ xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
     lx[j] = wl0[j];
     if (NCH > 1) lx[NX + j] = sl0[j];
   }
-  const long long q0 = (long long)blockIdx.x * T;
+  const long long q0 = (long long)bx * T;
   const int lvalid = (int)((plane - q0 < T) ? (plane - q0) : T);
-  C* base = spec + (long long)blockIdx.y * NCH * NX * plane + q0;
+  C* base = spec + (long long)by * NCH * NX * plane + q0;
   // per-thread (y,z) part of the symbol
   const int l = tid % T;
   R wy = R(0), wz = R(0), sy = R(0), sz = R(0);
@@ -973,7 +977,7 @@ struct FastLaunch {
     dim3 grid((unsigned)cdiv(plane, TX), (unsigned)(NCH == 1 ? N * D : N));
     xpass2_kernel<R, NX, TX, D, NCH, INVERSE><<<grid, kFftThreads, smem, s>>>(
         spec, plane, Zc, (const C*)p.tw[0], (const R*)p.wl[0], (const R*)p.sl[0], (const R*)p.wl[1],
-        (const R*)p.sl[1], (const R*)p.wl[2], (const R*)p.sl[2], alpha, beta, gamma, scale);
+        (const R*)p.sl[1], (const R*)p.wl[2], (const R*)p.sl[2], alpha, beta, gamma, scale, rev_hint());
     count_launch("xpass", s);
     return LGM_OK;
   }
@@ -1022,11 +1026,11 @@ static int slab_launch(bool inv, void* real, typename Cx<R>::T* spec, long long 
   const size_t smem = sizeof(C) * ((size_t)(M + 1) * (YZ + 1) + YZ + M + YZ);
   if (!inv) {
     LGM_CUDA_TRY(set_smem(slab_fwd_kernel<R, YZ, YZ>, smem), "slab_fwd smem");
-    slab_fwd_kernel<R, YZ, YZ><<<(unsigned)slabs, kFftThreads, smem, s>>>(spec, (const R*)real, (const C*)p.tw[2], (const C*)p.tw[1]);
+    slab_fwd_kernel<R, YZ, YZ><<<(unsigned)slabs, kFftThreads, smem, s>>>(spec, (const R*)real, (const C*)p.tw[2], (const C*)p.tw[1], rev_hint());
     count_launch("slab_fwd", s);
   } else {
     LGM_CUDA_TRY(set_smem(slab_inv_kernel<R, YZ, YZ>, smem), "slab_inv smem");
-    slab_inv_kernel<R, YZ, YZ><<<(unsigned)slabs, kFftThreads, smem, s>>>((R*)real, spec, (const C*)p.tw[2], (const C*)p.tw[1]);
+    slab_inv_kernel<R, YZ, YZ><<<(unsigned)slabs, kFftThreads, smem, s>>>((R*)real, spec, (const C*)p.tw[2], (const C*)p.tw[1], rev_hint());
     count_launch("slab_inv", s);
   }
   return LGM_OK;
@@ -1041,12 +1045,12 @@ static int cslab_launch(bool inv, void* real, float2* spec, long long slabs, con
   const size_t smem = sizeof(float2) * ((size_t)kCsRows * kCsP + 256 + 128 + 256);
   if (!inv) {
     if (set_smem(cslab_fwd_kernel, smem) != cudaSuccess) { cudaGetLastError(); broken = true; return LGM_EUNSUP; }
-    cslab_fwd_kernel<<<(unsigned)(kCsNC * slabs), kCsThreads, smem, s>>>(spec, (const float*)real, (const float2*)p.tw[2], (const float2*)p.tw[1]);
+    cslab_fwd_kernel<<<(unsigned)(kCsNC * slabs), kCsThreads, smem, s>>>(spec, (const float*)real, (const float2*)p.tw[2], (const float2*)p.tw[1], rev_hint());
     if (cudaPeekAtLastError() != cudaSuccess) { cudaGetLastError(); broken = true; return LGM_EUNSUP; }
     count_launch("slab_fwd", s);
   } else {
     if (set_smem(cslab_inv_kernel, smem) != cudaSuccess) { cudaGetLastError(); broken = true; return LGM_EUNSUP; }
-    cslab_inv_kernel<<<(unsigned)(kCsNC * slabs), kCsThreads, smem, s>>>((float*)real, spec, (const float2*)p.tw[2], (const float2*)p.tw[1]);
+    cslab_inv_kernel<<<(unsigned)(kCsNC * slabs), kCsThreads, smem, s>>>((float*)real, spec, (const float2*)p.tw[2], (const float2*)p.tw[1], rev_hint());
     if (cudaPeekAtLastError() != cudaSuccess) { cudaGetLastError(); broken = true; return LGM_EUNSUP; }
     count_launch("slab_inv", s);
   }
@@ -1071,6 +1075,11 @@ static int slab_pass(bool inv, int Y, int Z, void* real, typename Cx<R>::T* spec
 
 // Subjects are pushed through all passes in chunks small enough for the chunk's spectrum to stay
 // resident in the 126 MB L2, so that only the first read and the last write of a chunk go to HBM.
+static bool alternate_passes() {
+  static const bool on = getenv("LGM_NO_ALTERNATE") == nullptr;  // kernel experiments
+  return on;
+}
+
 static long long chunk_budget_bytes() {
   static long long v = -1;
   if (v < 0) {
@@ -1106,6 +1115,7 @@ static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64
     R* out_g = (R*)out + n0 * dim * V;
     const long long rows = g * dim * (V / nlast);
     int rc = LGM_EUNSUP;
+    const int rev0 = rev_hint();  // forward slab: as hinted; X pass: opposite; inverse slab: as hinted
     if (dim == 3) rc = slab_pass<R>(false, Y, nlast, (void*)in_g, spec, g * dim * X, p, s);
     const bool slab = (rc == LGM_OK);
     if (rc != LGM_OK && rc != LGM_EUNSUP) return rc;
@@ -1121,7 +1131,9 @@ static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64
         if (rc) return rc;
       }
       rc = LGM_EUNSUP;
+      if (alternate_passes()) rev_hint() = !rev0;
       LGM_SWITCH_POW2(X, MAXN, rc = (FL::template xpass<NN, 3>(spec, g, (long long)Y * Zc, Zc, p, inverse, alpha, beta, gamma, scale, s)));
+      rev_hint() = rev0;
       if (rc) return rc;
       if (!slab) {
         rc = LGM_EUNSUP;

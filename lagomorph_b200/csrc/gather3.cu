@@ -46,14 +46,17 @@ namespace lgm {
 template <int MODE, int NV, int BX>
 __global__ void __launch_bounds__(256, MODE == 0 ? LGM_ADSTAR_MINB : LGM_COMPOSE_MINB)
 gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
-               int X, int Y, int Z, float dh, float dl, float dsr, float dtr) {
+               int X, int Y, int Z, float dh, float dl, float dsr, float dtr, int rev) {
   // blockDim = (32, 8/BX, BX): BX neighbouring x slabs share a CTA so that the upper-x corner rows
   // of one slab are the lower-x rows of the next (L1 reuse instead of a second L2 fetch)
-  const int j = blockIdx.y * (8 / BX) + threadIdx.y;
+  // rev: walk the grid from its far end (see rev_hint() in common.cuh)
+  const unsigned bz = rev ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
+  const unsigned by = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int j = by * (8 / BX) + threadIdx.y;
   const int XB = (X + BX - 1) / BX;
-  const int i = (blockIdx.z % XB) * BX + threadIdx.z;
+  const int i = (bz % XB) * BX + threadIdx.z;
   if (j >= Y || i >= X) return;
-  const int n = blockIdx.z / XB;
+  const int n = bz / XB;
   const int sy = Z, sx = Y * Z;
   const int V = X * sx;
   const float* an = a + (size_t)n * 3 * V;
@@ -361,7 +364,7 @@ int Ad_star3_f32(void* out, const void* phi, const void* m, int64_t N, const int
   constexpr int BX = LGM_GATHER_BX;
   dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8 / BX), (unsigned)(N * cdiv(sh[0], BX))), block(32, 8 / BX, BX);
   gather3_kernel<0, 4, BX><<<grid, block, 0, s>>>((float*)out, (const float*)phi, (const float*)m, (int)sh[0],
-                                           (int)sh[1], (int)sh[2], 1.f, 0.f, 0.f, 0.f);
+                                           (int)sh[1], (int)sh[2], 1.f, 0.f, 0.f, 0.f, rev_hint());
   count_launch("Ad_star", s);
   return finish(s, "lgm_Ad_star_fwd");
 }
@@ -373,7 +376,7 @@ int compose3_f32(void* out, const void* u, const void* v, int64_t N, const int64
   constexpr int BX = LGM_GATHER_BX;
   dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8 / BX), (unsigned)(N * cdiv(sh[0], BX))), block(32, 8 / BX, BX);
   gather3_kernel<1, 4, BX><<<grid, block, 0, s>>>((float*)out, (const float*)u, (const float*)v, (int)sh[0],
-                                           (int)sh[1], (int)sh[2], dh, dl, (float)ds, (float)dt);
+                                           (int)sh[1], (int)sh[2], dh, dl, (float)ds, (float)dt, rev_hint());
   count_launch("compose", s);
   return finish(s, "lgm_compose_fwd");
 }
