@@ -174,11 +174,21 @@ affine_bwd_kernel(R* __restrict__ d_I, R* __restrict__ d_A, R* __restrict__ d_T,
   }
 }
 
+// fp32 3-D fast paths (affine3.cu); LGM_EUNSUP = not applicable
+int affine3_fwd_f32(void* out, const void* I, const void* A, const void* T, int64_t N, int64_t NI, int64_t C,
+                    const int64_t* sh, cudaStream_t s);
+int affine3_bwd_f32(void* d_I, void* d_A, void* d_T, const void* go, const void* I, const void* A, const void* T,
+                    int64_t N, int64_t NI, int64_t C, const int64_t* sh, cudaStream_t s);
+
 template <typename R, int D>
 static int affine_fwd_t(void* out, const void* I, const void* A, const void* T, int64_t N,
                         int64_t NI, int64_t C, const int64_t* shape, cudaStream_t s) {
   Geom<D> g = make_geom<D>(shape);
   if (g.V == 0 || N == 0 || C == 0) return LGM_OK;
+  if constexpr (sizeof(R) == 4 && D == 3) {
+    int rc = affine3_fwd_f32(out, I, A, T, N, NI, C, shape, s);
+    if (rc != LGM_EUNSUP) return rc;
+  }
   dim3 grid((unsigned)cdiv(g.V, kThreads), (unsigned)N);
   const long long ibs = (NI == 1 && N > 1) ? 0 : C * g.V;
   affine_fwd_kernel<R, D><<<grid, kThreads, 0, s>>>((R*)out, (const R*)I, (const R*)A, (const R*)T, g, (int)C, ibs);
@@ -197,6 +207,10 @@ static int affine_bwd_t(void* d_I, void* d_A, void* d_T, const void* go, const v
   if (e == cudaSuccess && d_T) e = cudaMemsetAsync(d_T, 0, (size_t)(N * D) * sizeof(R), s);
   if (e != cudaSuccess) return set_error((int)e, "lgm_affine_interp_bwd: memset: %s", cudaGetErrorString(e));
   if (g.V == 0 || N == 0 || C == 0 || (!d_I && !d_A && !d_T)) return LGM_OK;
+  if constexpr (sizeof(R) == 4 && D == 3) {
+    int rc = affine3_bwd_f32(d_I, d_A, d_T, go, I, A, T, N, NI, C, shape, s);
+    if (rc != LGM_EUNSUP) return rc;
+  }
   dim3 grid((unsigned)cdiv(g.V, kThreads), (unsigned)N);
   const long long ibs = (NI == 1 && N > 1) ? 0 : C * g.V;
   const bool need_at = d_A || d_T;

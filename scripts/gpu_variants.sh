@@ -1,5 +1,8 @@
-python scripts/variant_bench.py c2 2>&1 | grep -v Warning | tee gpurun_out/variants.log
-LGM_NO_ALTERNATE=1 python scripts/variant_bench.py c2 2>&1 | grep -v Warning | tee -a gpurun_out/variants.log
-python scripts/variant_bench.py c3 2>&1 | grep -v Warning | tee -a gpurun_out/variants.log
-LGM_NO_ALTERNATE=1 python scripts/variant_bench.py c3 2>&1 | grep -v Warning | tee -a gpurun_out/variants.log
-(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3) | tee gpurun_out/pytest_gpu.log
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -12) | tee gpurun_out/pytest_gpu.log
+python bench_ops.py > gpurun_out/ops.json 2> gpurun_out/ops.err
+python -c "
+import json
+d=json.load(open('gpurun_out/ops.json'))
+for k,v in d['ops'].items():
+    if 'affine' in k or 'interp' in k: print('%-48s %.4f ms  %.3f' % (k, v['ms'], v['frac_of_hbm_peak']))
+"

@@ -225,6 +225,34 @@ def test_affine_interp_forward(lm, orc, dim, dtype, bcast):
     assert relerr(out, ref) <= (5e-5 if dtype == torch.float32 else 1e-12)
 
 
+@pytest.mark.parametrize("bcast", [False, True])
+@pytest.mark.parametrize("C", [1, 2])
+def test_affine_interp_fast_paths_3d(lm, orc, bcast, C):
+    """fp32 3-D fast kernels (csrc/affine3.cu; the backward one needs Z % 32 == 0): forward against the
+    oracle, all three gradients against the fp64 generic kernels on the same inputs (incl. samples
+    pushed outside the volume by the rotation / translation)"""
+    sh = (6, 10, 32)
+    N = 3
+    I = randn((1 if bcast else N, C) + sh, torch.float32, 94)
+    A = torch.eye(3).repeat(N, 1, 1) + randn((N, 3, 3), torch.float32, 95, 0.1)
+    T = randn((N, 3), torch.float32, 96, 1.5)
+    go = randn((N, C) + sh, torch.float32, 97)
+    assert relerr(lm.affine_interp(I.cuda(), A.cuda(), T.cuda()), orc.affine_interp_forward(I, A, T)) <= 5e-5
+    grads = {}
+    for dt in (torch.float32, torch.float64):
+        Ic, Ac, Tc = (t.to(dt).cuda().requires_grad_(True) for t in (I, A, T))
+        grads[dt] = torch.autograd.grad(lm.affine_interp(Ic, Ac, Tc), [Ic, Ac, Tc], go.to(dt).cuda())
+    for g32, g64 in zip(grads[torch.float32], grads[torch.float64]):
+        assert relerr(g32.double(), g64) <= 1e-4
+    # single gradients take other template instances (d_I only / d_A, d_T only)
+    Ic, Ac, Tc = (t.cuda().requires_grad_(True) for t in (I, A, T))
+    out = lm.affine_interp(Ic, Ac, Tc)
+    (dI,) = torch.autograd.grad(out, [Ic], go.cuda(), retain_graph=True)
+    dA, dT = torch.autograd.grad(out, [Ac, Tc], go.cuda())
+    assert relerr(dI.double(), grads[torch.float64][0]) <= 1e-4
+    assert relerr(dA.double(), grads[torch.float64][1]) <= 1e-4 and relerr(dT.double(), grads[torch.float64][2]) <= 1e-4
+
+
 def test_empty_and_errors(lm):
     z = torch.zeros(0, 3, 4, 4, 4, device="cuda")
     assert lm.interp(z, z).shape == z.shape
