@@ -32,6 +32,12 @@
 #else
 #define LGM_LDC(p) __ldg(p)
 #endif
+#ifndef LGM_GATHER_NR
+#define LGM_GATHER_NR 1  /* y rows per thread in Ad_star / compose */
+#endif
+#ifndef LGM_GATHER_NV
+#define LGM_GATHER_NV 4  /* 32-voxel chunks of a z row per thread in Ad_star / compose */
+#endif
 #ifndef LGM_COMPOSE_MINB
 #define LGM_COMPOSE_MINB 5
 #endif
@@ -43,7 +49,7 @@ namespace lgm {
 
 // MODE 0: Ad_star (a = phiinv, b = m0); MODE 1: compose (a = u, b = v).
 // blockDim = (32, 8): a warp walks one z row (lane = z, NV chunks of 32), a CTA covers 8 y rows.
-template <int MODE, int NV, int BX>
+template <int MODE, int NV, int BX, int NR>
 __global__ void __launch_bounds__(256, MODE == 0 ? LGM_ADSTAR_MINB : LGM_COMPOSE_MINB)
 gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b,
                int X, int Y, int Z, float dh, float dl, float dsr, float dtr, int rev) {
@@ -52,7 +58,8 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
   // rev: walk the grid from its far end (see rev_hint() in common.cuh)
   const unsigned bz = rev ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
   const unsigned by = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
-  const int j = by * (8 / BX) + threadIdx.y;
+  // a thread owns NR rows (j, j + 8/BX, ...) x NV chunks: NR * NV voxels, all centre loads up front
+  const int j = by * (8 / BX) * NR + threadIdx.y;
   const int XB = (X + BX - 1) / BX;
   const int i = (bz % XB) * BX + threadIdx.z;
   if (j >= Y || i >= X) return;
@@ -76,28 +83,34 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
   asm volatile("" : "+l"(on), "+l"(on1), "+l"(on2));
   const unsigned four = opaque_four();
   const float hiX = (float)X - 0.5f, hiY = (float)Y - 0.5f, hiZ = (float)Z - 0.5f;
-  const int row = i * sx + j * sy;
-  const float fi = (float)i, fj = (float)j;
+  const int row0 = i * sx + j * sy;
+  const float fi = (float)i;
   const int xm = (i > 0) ? -sx : 0, xp = (i < X - 1) ? sx : 0;
-  const int ym = (j > 0) ? -sy : 0, yp = (j < Y - 1) ? sy : 0;
   // the centre loads of ALL chunks are issued up front: they gate everything else of a chunk, and
   // 3*NV registers buy one full memory round trip of overlap per chunk
-  float Apre[NV][3];
+  float Apre[NR * NV][3];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
+  for (int sl = 0; sl < NR * NV; ++sl) {
+    const int r = sl / NV, v = sl % NV;
     const int k = (blockIdx.x * NV + v) * 32 + threadIdx.x;
-    if (k < Z) {
-      Apre[v][0] = LGM_LDC(an + (row + k));  // literal addressing: must not wait for `four`
-      Apre[v][1] = LGM_LDC(an1 + (row + k));
-      Apre[v][2] = LGM_LDC(an2 + (row + k));
+    const int row = row0 + r * (8 / BX) * sy;
+    if (k < Z && j + r * (8 / BX) < Y) {
+      Apre[sl][0] = LGM_LDC(an + (row + k));  // literal addressing: must not wait for `four`
+      Apre[sl][1] = LGM_LDC(an1 + (row + k));
+      Apre[sl][2] = LGM_LDC(an2 + (row + k));
     }
   }
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
+  for (int sl = 0; sl < NR * NV; ++sl) {
+    const int r = sl / NV, v = sl % NV;
     const int k = (blockIdx.x * NV + v) * 32 + threadIdx.x;
-    if (k >= Z) break;
+    const int jr = j + r * (8 / BX);
+    if (k >= Z || jr >= Y) continue;
+    const int row = row0 + r * (8 / BX) * sy;
+    const float fj = (float)jr;
+    const int ym = (jr > 0) ? -sy : 0, yp = (jr < Y - 1) ? sy : 0;
     const int c0 = row + k;
-    const float A0 = Apre[v][0], A1 = Apre[v][1], A2 = Apre[v][2];
+    const float A0 = Apre[sl][0], A1 = Apre[sl][1], A2 = Apre[sl][2];
     float hx, hy, hz;
     const float fk = (float)k;
     if (MODE == 0) {  // dt == 1: the double sum is exact before rounding
@@ -362,8 +375,8 @@ static bool fast3_ok(const void* p0, const void* p1, const void* p2, int64_t N, 
 int Ad_star3_f32(void* out, const void* phi, const void* m, int64_t N, const int64_t* sh, cudaStream_t s) {
   if (!fast3_ok(out, phi, m, N, sh)) return LGM_EUNSUP;
   constexpr int BX = LGM_GATHER_BX;
-  dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8 / BX), (unsigned)(N * cdiv(sh[0], BX))), block(32, 8 / BX, BX);
-  gather3_kernel<0, 4, BX><<<grid, block, 0, s>>>((float*)out, (const float*)phi, (const float*)m, (int)sh[0],
+  dim3 grid((unsigned)cdiv(sh[2], 32 * LGM_GATHER_NV), (unsigned)cdiv(sh[1], (8 / BX) * LGM_GATHER_NR), (unsigned)(N * cdiv(sh[0], BX))), block(32, 8 / BX, BX);
+  gather3_kernel<0, LGM_GATHER_NV, BX, LGM_GATHER_NR><<<grid, block, 0, s>>>((float*)out, (const float*)phi, (const float*)m, (int)sh[0],
                                            (int)sh[1], (int)sh[2], 1.f, 0.f, 0.f, 0.f, rev_hint());
   count_launch("Ad_star", s);
   return finish(s, "lgm_Ad_star_fwd");
@@ -374,8 +387,8 @@ int compose3_f32(void* out, const void* u, const void* v, int64_t N, const int64
   if (!fast3_ok(out, u, v, N, sh)) return LGM_EUNSUP;
   const float dh = (float)ds, dl = (float)(ds - (double)dh);
   constexpr int BX = LGM_GATHER_BX;
-  dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8 / BX), (unsigned)(N * cdiv(sh[0], BX))), block(32, 8 / BX, BX);
-  gather3_kernel<1, 4, BX><<<grid, block, 0, s>>>((float*)out, (const float*)u, (const float*)v, (int)sh[0],
+  dim3 grid((unsigned)cdiv(sh[2], 32 * LGM_GATHER_NV), (unsigned)cdiv(sh[1], (8 / BX) * LGM_GATHER_NR), (unsigned)(N * cdiv(sh[0], BX))), block(32, 8 / BX, BX);
+  gather3_kernel<1, LGM_GATHER_NV, BX, LGM_GATHER_NR><<<grid, block, 0, s>>>((float*)out, (const float*)u, (const float*)v, (int)sh[0],
                                            (int)sh[1], (int)sh[2], dh, dl, (float)ds, (float)dt, rev_hint());
   count_launch("compose", s);
   return finish(s, "lgm_compose_fwd");

@@ -1,8 +1,5 @@
-(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -12) | tee gpurun_out/pytest_gpu.log
-python bench_ops.py > gpurun_out/ops.json 2> gpurun_out/ops.err
-python -c "
-import json
-d=json.load(open('gpurun_out/ops.json'))
-for k,v in d['ops'].items():
-    if 'affine' in k or 'interp' in k: print('%-48s %.4f ms  %.3f' % (k, v['ms'], v['frac_of_hbm_peak']))
-"
+for v in "" nr2 nr4; do
+  if [ -n "$v" ]; then export LGM_LIB_PATH=$PWD/lagomorph_b200/variants/lib_$v.so; else unset LGM_LIB_PATH; fi
+  python scripts/variant_bench.py c2
+done 2>&1 | grep -v Warning | tee gpurun_out/variants.log
+LGM_LIB_PATH=$PWD/lagomorph_b200/variants/lib_nr2.so timeout 600 python -m pytest tests -m gpu -x -q -k "adjrep or fullsize or golden or expmap" 2>&1 | tail -2
