@@ -268,6 +268,9 @@ static int get_plan(int dim, const int64_t* shape, cudaStream_t s, const FluidPl
 #endif
 constexpr int kFftThreads = LGM_FFT_THREADS;
 constexpr int kSlabIoUnroll = LGM_SLAB_IO_UNROLL;
+#ifndef LGM_XPASS_TX32_MAX
+#define LGM_XPASS_TX32_MAX 128  /* largest NCH*NX whose X-pass tile is 32 words wide (else 16) */
+#endif
 #ifndef LGM_XPASS_MINBLOCKS
 #define LGM_XPASS_MINBLOCKS 4  /* 64 registers: measured 0.254 -> 0.240 ms per C2 X pass vs 80 registers */
 #endif
@@ -971,7 +974,7 @@ struct FastLaunch {
   static int xpass1(C* spec, long long N, long long plane, int Zc, const FluidPlan& p, double alpha,
                     double beta, double gamma, R scale, cudaStream_t s) {
     // tile width: 32 words (256 B runs) while the tile stays small, else the class default
-    constexpr int TX = (sizeof(R) == 4 && NCH * NX <= 128) ? 32 : T;  // 32 at NX=256 measured slower (regs)
+    constexpr int TX = (sizeof(R) == 4 && NCH * NX <= LGM_XPASS_TX32_MAX) ? 32 : T;  // 32 at NX=256 measured slower (regs)
     const size_t smem = sizeof(C) * ((size_t)NCH * NX * TX + NX) + sizeof(R) * 2 * NX;
     LGM_CUDA_TRY(set_smem(xpass2_kernel<R, NX, TX, D, NCH, INVERSE>, smem), "xpass smem");
     dim3 grid((unsigned)cdiv(plane, TX), (unsigned)(NCH == 1 ? N * D : N));
