@@ -71,3 +71,22 @@ def test_shard_indices():
         for r in range(w):
             ds = DistributedSampler(list(range(n)), num_replicas=w, rank=r, shuffle=False)
             assert list(ds) == shard_indices(n, w, r)
+
+
+def test_expmap_host_chunk_schedule(lm):
+    """_auto_chunks: sizes are positive, add up to the batch, ramp up from one subject and down to one
+    when copies are faster than compute, and stay at one when they are not"""
+    from lagomorph_b200.lddmm import _auto_chunks
+    for steps in (1, 3, 5, 10, 20, 50):
+        for N in list(range(1, 40)) + [64, 100]:
+            c = _auto_chunks(N, steps)
+            assert sum(c) == N and min(c) >= 1, (N, steps, c)
+            assert c[0] == 1 and c[-1] == 1 or N <= 3, (N, steps, c)
+    assert _auto_chunks(16, 10) == [1, 2, 4, 5, 3, 1]
+    assert _auto_chunks(8, 5) == [1] * 8
+    with pytest.raises(RuntimeError, match="host tensors"):
+        lm.expmap_host(lm.FluidMetric(), torch.zeros(1, 3, 4, 4, 4, device="meta") if False else _FakeCuda())
+
+
+class _FakeCuda:
+    is_cuda = True
