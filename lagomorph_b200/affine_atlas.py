@@ -28,12 +28,15 @@ def _as_tensor_batch(dataset, ids, dtype, device):
 
 def affine_atlas(dataset, As, Ts, I=None, num_epochs=1000, batch_size=50, image_update_freq=0, affine_steps=1,
                  reg_weightA=0e1, reg_weightT=0e1, learning_rate_A=1e-3, learning_rate_T=1e-2,
-                 learning_rate_I=1e5, gpu=None, world_size=1, rank=0, device=None):
+                 learning_rate_I=1e5, gpu=None, world_size=1, rank=0, device=None, _interp=None):
     """dataset: tensor (S, 1, X, Y[, Z]) of all subjects or an indexable of (1, X, Y[, Z]) images;
     As (S, d, d) and Ts (S, d): the affine parameters (A is stored minus the identity, as in the
-    reference). Returns (I, As, Ts, epoch_losses, iter_losses) like lagomorph.affine.affine_atlas."""
+    reference). Returns (I, As, Ts, epoch_losses, iter_losses) like lagomorph.affine.affine_atlas.
+    `_interp`: test hook, a stand-in for affine_interp so that the sharding / accumulation / collective
+    bookkeeping can be exercised on CPU over gloo (tests/test_atlas_gloo.py); never used by the product."""
     dev = torch.device(device if device is not None else ("cuda:%d" % gpu if gpu is not None else "cuda"))
-    if dev.type != "cuda":
+    interp_fn = affine_interp if _interp is None else _interp
+    if dev.type != "cuda" and _interp is None:
         raise RuntimeError("affine_atlas: the affine_interp kernels are CUDA only (no CPU fallback)")
     S = len(dataset)
     ids = shard_indices(S, world_size, rank)
@@ -85,7 +88,7 @@ def affine_atlas(dataset, As, Ts, I=None, num_epochs=1000, batch_size=50, image_
                 T.grad = None
                 last = affit == affine_steps - 1         # the image gradient accumulates at the last affine step only
                 Iin = I if last else I.detach()
-                Idef = affine_interp(Iin, A + eye, T)
+                Idef = interp_fn(Iin, A + eye, T)
                 regloss = 0.0
                 if reg_weightA > 0:
                     regloss = regloss + 0.5 * reg_weightA * L2(A, A)

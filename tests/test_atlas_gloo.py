@@ -69,3 +69,48 @@ def test_two_ranks_match_one(tmp_path):
     assert torch.allclose(r["I"], I1, atol=1e-6)
     assert torch.allclose(torch.tensor(r["losses"]), torch.tensor(single.epoch_losses), atol=1e-6)
     assert torch.allclose(torch.tensor(r["regs"]), torch.tensor(single.epoch_reg_terms), atol=1e-6)
+
+
+# ---- affine atlas (lagomorph_b200/affine_atlas.py) ------------------------------------------------------
+def _fake_affine_interp(I, A, T):
+    # differentiable stand-in with the right shapes: per-subject gain and offset from (A, T)
+    gain = A.diagonal(dim1=1, dim2=2).mean(1).view(-1, 1, 1, 1)
+    off = 0.1 * T.sum(1).view(-1, 1, 1, 1) + 0.05 * A.sum((1, 2)).view(-1, 1, 1, 1)
+    return I * gain + off
+
+
+_AFF_KW = dict(num_epochs=3, batch_size=2, learning_rate_A=0.05, learning_rate_T=0.5, learning_rate_I=0.3,
+               reg_weightA=0.1, reg_weightT=0.05, device="cpu", _interp=_fake_affine_interp)
+
+
+def _affine_worker(rank, world_size, port, data, As, Ts, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    from lagomorph_b200.affine_atlas import affine_atlas
+    I, A, T, el, il = affine_atlas(data, As.clone(), Ts.clone(), world_size=world_size, rank=rank, **_AFF_KW)
+    if rank == 0:
+        torch.save({"I": I, "A": A, "T": T, "el": el}, out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_affine_atlas_two_ranks_match_one(tmp_path):
+    """2 ranks x 4 subjects (batches of 2) == one process over the same subjects in DistributedSampler
+    order (rank 0: subjects 0,2,4,6; rank 1: 1,3,5,7): same atlas, poses and epoch losses. With
+    image_update_freq = 0 the single process averages the image gradient over its 4 batches, the two
+    ranks over 2 batches each and then over the ranks: the same number."""
+    from lagomorph_b200.affine_atlas import affine_atlas
+    torch.manual_seed(2)
+    S = 8
+    data = torch.randn(S, 1, 6, 5)
+    As, Ts = 0.1 * torch.randn(S, 2, 2), 0.3 * torch.randn(S, 2)
+    perm = [0, 2, 4, 6, 1, 3, 5, 7]
+    I1, A1, T1, el1, _ = affine_atlas(data[perm], As[perm].clone(), Ts[perm].clone(), **_AFF_KW)
+    inv = torch.argsort(torch.tensor(perm))
+    out = str(tmp_path / "aff.pt")
+    mp.spawn(_affine_worker, args=(2, _free_port(), data, As, Ts, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert torch.allclose(r["I"], I1, atol=1e-6)
+    assert torch.allclose(r["A"], A1[inv], atol=1e-6) and torch.allclose(r["T"], T1[inv], atol=1e-6)
+    assert torch.allclose(torch.tensor(r["el"]), torch.tensor(el1), atol=1e-6)
