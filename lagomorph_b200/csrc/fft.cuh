@@ -258,6 +258,43 @@ __device__ __forceinline__ void fft_mid_stage(typename Cx<R>::T* tile, int rs, i
   }
 }
 
+// fft_mid_stage for NCH coupled channels (tiles `chs` words apart): the multiplier sees the NCH values
+// of one (row, line) together (the matrix-valued Fourier symbol of the fluid operator with beta != 0).
+template <typename R, int N, int RAD, int L, int NCH, typename F>
+__device__ __forceinline__ void fft_mid_stage_multi(typename Cx<R>::T* tile, int chs, int rs, int ls, int tid,
+                                                    int nth, F mult) {
+  using C = typename Cx<R>::T;
+  constexpr int ITEMS = L * (N / RAD);
+  constexpr int BITS = ilog2(RAD);
+  for (int it = tid; it < ITEMS; it += nth) {
+    const int l = it % L, blk = it / L;
+    C* p = tile + blk * RAD * rs + l * ls;
+    C x[NCH][RAD];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+      for (int n = 0; n < RAD; ++n) x[c][n] = p[c * chs + n * rs];
+      reg_fft<RAD, false>(x[c]);
+    }
+    C y[NCH][RAD];
+#pragma unroll
+    for (int k = 0; k < RAD; ++k) {
+      C v[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) v[c] = x[c][bitrev(k, BITS)];
+      mult(blk * RAD + k, l, v);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) y[c][k] = v[c];
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      reg_fft<RAD, true>(y[c]);
+#pragma unroll
+      for (int i = 0; i < RAD; ++i) p[c * chs + bitrev(i, BITS) * rs] = y[c][i];
+    }
+  }
+}
+
 // Outermost stage (BLOCK == N) with one side in GLOBAL memory: the forward transform's first
 // stage reads its RAD inputs straight from global memory (row stride grs, lanes along l are
 // consecutive words => coalesced) and stores to the shared tile; the inverse transform's last

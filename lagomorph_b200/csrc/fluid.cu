@@ -268,6 +268,9 @@ static int get_plan(int dim, const int64_t* shape, cudaStream_t s, const FluidPl
 #endif
 constexpr int kFftThreads = LGM_FFT_THREADS;
 constexpr int kSlabIoUnroll = LGM_SLAB_IO_UNROLL;
+#ifndef LGM_XPASS_MULTI_RADMAX
+#define LGM_XPASS_MULTI_RADMAX 8  /* largest innermost radix fused in registers for beta != 0 (3 channels) */
+#endif
 #ifndef LGM_XPASS_TX32_MAX
 #define LGM_XPASS_TX32_MAX 128  /* largest NCH*NX whose X-pass tile is 32 words wide (else 16) */
 #endif
@@ -796,6 +799,49 @@ xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
       __syncthreads();
     }
     fft_stage_edge<R, NX, RAD0, T, true>(base, plane, tile, T, 1, tw, lvalid, tid, kFftThreads);
+  } else if constexpr (sizeof(R) == 4 && NCH > 1 && NS >= 2 && (1 << stage_bits(ilog2(NX), NS - 1)) <= LGM_XPASS_MULTI_RADMAX) {
+    // beta != 0 with a small innermost radix: the same register fusion for the NCH coupled channels
+    // (the matrix symbol is built once per frequency and applied to the real and imaginary parts)
+    constexpr int RAD0 = 1 << stage_bits(ilog2(NX), 0);
+    constexpr int RADL = 1 << stage_bits(ilog2(NX), NS - 1);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+      fft_stage_edge<R, NX, RAD0, T, false>(base + (long long)ch * NX * plane, plane, tile + ch * NX * T, T, 1, tw,
+                                            lvalid, tid, kFftThreads);
+    __syncthreads();
+    if constexpr (NS > 2) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) ColFFT<R, NX, NX / RAD0, 1, T>::fwd_nolast(tile + ch * NX * T, T, 1, tw, tid, kFftThreads);
+      __syncthreads();
+    }
+    fft_mid_stage_multi<R, NX, RADL, T, NCH>(tile, NX * T, T, 1, tid, kFftThreads, [&](int r, int, C (&v)[NCH]) {
+      R w[3] = {lx[r], wy, wz};
+      R sn[3] = {lx[NX + r], sy, sz};
+      Symbol<R, D> S = make_symbol<R, D, INVERSE>(w, sn, alpha, beta, gamma);
+      R re[D], im[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        re[c] = v[c].x;
+        im[c] = v[c].y;
+      }
+      apply_symbol<R, D, INVERSE>(S, re);
+      apply_symbol<R, D, INVERSE>(S, im);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        v[c].x = re[c] * scale;
+        v[c].y = im[c] * scale;
+      }
+    });
+    __syncthreads();
+    if constexpr (NS > 2) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) ColFFT<R, NX, NX / RAD0, 1, T>::inv_nolast(tile + ch * NX * T, T, 1, tw, tid, kFftThreads);
+      __syncthreads();
+    }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+      fft_stage_edge<R, NX, RAD0, T, true>(base + (long long)ch * NX * plane, plane, tile + ch * NX * T, T, 1, tw,
+                                           lvalid, tid, kFftThreads);
   } else {
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch)
