@@ -148,6 +148,16 @@ int lgm_epdiff_step_fwd(int dtype, void* phiinv_out, const void* phiinv, const v
                         const void* mommask, int64_t N, int dim, const int64_t* shape, double dt,
                         double alpha, double beta, double gamma, void* scratch,
                         int64_t scratch_bytes, void* stream);
+/* The whole forward shoot, expmap without autograd (lagomorph/lddmm.py:73-91, the loop :87-91):
+ *   phiinv_0 = phiinv_in (NULL: zeros, lddmm.py:84-85); num_steps times lgm_epdiff_step_fwd.
+ * Same kernels and results as that loop; one call per shoot (no per-step host work, explicit
+ * traversal directions alternating from step to step, CUDA-graph capturable).
+ * scratch: lgm_expmap_scratch_bytes() bytes. phiinv_out must not alias phiinv_in. */
+int64_t lgm_expmap_scratch_bytes(int dtype, int64_t N, int dim, const int64_t* shape);
+int lgm_expmap_fwd(int dtype, void* phiinv_out, const void* phiinv_in, const void* m0,
+                   const void* mommask, int64_t N, int dim, const int64_t* shape, double dt,
+                   int num_steps, double alpha, double beta, double gamma, void* scratch,
+                   int64_t scratch_bytes, void* stream);
 /* Backward of one EPDiff step: what autograd does for lddmm.py:39-44 through
  * InterpFunction.backward (deform.py:31-41), JacobianTimesVectorFieldFunction.backward
  * (diff.py:29-35) and FluidMetricOperator.backward (metric.py:21-34), as three fused kernels

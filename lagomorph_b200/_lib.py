@@ -48,6 +48,8 @@ SIGNATURES = {
     "lgm_compose_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64_p, c_double, c_double, c_void_p]),
     "lgm_epdiff_scratch_bytes": (c_i64, [c_int, c_i64, c_int, c_i64_p]),
     "lgm_epdiff_step_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64_p, c_double, c_double, c_double, c_double, c_void_p, c_i64, c_void_p]),
+    "lgm_expmap_scratch_bytes": (c_i64, [c_int, c_i64, c_int, c_i64_p]),
+    "lgm_expmap_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64_p, c_double, c_int, c_double, c_double, c_double, c_void_p, c_i64, c_void_p]),
     "lgm_epdiff_bwd_scratch_bytes": (c_i64, [c_int, c_i64, c_int, c_i64_p]),
     "lgm_epdiff_step_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64_p, c_double, c_double, c_double, c_double, c_void_p, c_i64, c_int, c_int, c_void_p]),
 }

@@ -7,8 +7,8 @@ those of the reference's unfused compositions.
 import torch
 
 from . import _lib as L
-from .deform import interp_backward, interp_forward
-from .diff import (jtvf_adjoint_backward, jtvf_backward, jtvf_forward)
+from .deform import interp, interp_backward, interp_forward
+from .diff import (jacobian_times_vectorfield, jtvf_adjoint_backward, jtvf_backward, jtvf_forward)
 
 
 def _fused(fn, a, b):
@@ -89,7 +89,11 @@ def ad_star(v, m):
 
 def Ad_star(phiinv, m):
     r"""Ad^*(phi,m)(x) = (D phi^{-1}(x) + I) m(x + phi^{-1}(x)) as the reference computes it:
-    jacobian_times_vectorfield(phiinv, interp(m, phiinv), displacement=True) (adjrep.py:86-97)."""
+    jacobian_times_vectorfield(phiinv, interp(m, phiinv), displacement=True) (adjrep.py:86-97).
+    A momentum of batch 1 broadcasts against N deformations like the reference's interp does
+    (cuda/interp.cu:90-92); that case runs the two-kernel composition, equal batches the fused kernel."""
+    if m.dim() == phiinv.dim() and m.shape[0] != phiinv.shape[0] and m.shape[1:] == phiinv.shape[1:]:
+        return jacobian_times_vectorfield(phiinv, interp(m, phiinv), displacement=True)
     return _AdStarBigFunction.apply(phiinv, m)
 
 

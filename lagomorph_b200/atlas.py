@@ -4,7 +4,7 @@ lagomorph/lddmm.py:108-375 for in-memory data).
 What is kept from the reference: the per-batch step (expmap -> deform atlas -> MSE + reg ->
 backward -> momentum update, lddmm.py:300-325), the loss normalisation, the SGD update of the
 atlas image with the all-reduced, averaged gradient (lddmm.py:287-298), subject sharding in
-DistributedSampler order (subject i -> rank i mod world_size, lddmm.py:163-178).
+the reference's DistributedSampler order (seed-0 permutation, strided by rank: lddmm.py:163-178).
 
 What is different (B200-first): momenta stay resident on the owning GPU instead of a pinned-host
 round trip per iteration (lddmm.py:236,328,337); the two scalar all_reduces are one 2-element
@@ -20,10 +20,18 @@ from .lddmm import expmap
 from .metric import FluidMetric
 
 
-def shard_indices(num_subjects, world_size, rank):
-    """DistributedSampler(shuffle=False, drop_last=False) order: pad by wrapping, stride by rank."""
+def shard_indices(num_subjects, world_size, rank, shuffle=True, seed=0):
+    """Subjects of one rank, in the order the reference's loader yields them (lddmm.py:163-178):
+    one process -> sequential (sampler=None, shuffle=False); several -> DistributedSampler(dataset,
+    num_replicas, rank) with its DEFAULT shuffle=True, seed 0 and epoch 0 (the reference never calls
+    set_epoch, so every epoch uses the same permutation): randperm(seed), padded by wrapping to a
+    multiple of world_size, strided by rank. shuffle=False gives the plain strided order."""
     idx = list(range(num_subjects))
     if world_size > 1:
+        if shuffle:
+            g = torch.Generator()
+            g.manual_seed(seed)
+            idx = torch.randperm(num_subjects, generator=g).tolist()
         total = (num_subjects + world_size - 1) // world_size * world_size
         idx = (idx + idx[: total - num_subjects])[rank:total:world_size]
     return idx
@@ -33,7 +41,7 @@ class LDDMMAtlasBuilder:
     def __init__(self, dataset, I0=None, ms=None, num_epochs=500, batch_size=10, lddmm_steps=1,
                  lddmm_integration_steps=5, image_update_freq=0, reg_weight=1e2, learning_rate_pose=2e2,
                  learning_rate_image=1e4, metric=None, momentum_shape=None, image_shape=None,
-                 momentum_preconditioning=False, device="cuda", world_size=1, rank=0):
+                 momentum_preconditioning=False, device="cuda", world_size=1, rank=0, checkpoint_format=None):
         """dataset: tensor (S, 1, X, Y[, Z]) of ALL subjects (each rank keeps its shard), or any
         indexable of (1, X, Y[, Z]) images."""
         self.dataset = dataset
@@ -48,7 +56,10 @@ class LDDMMAtlasBuilder:
         self.momentum_preconditioning = momentum_preconditioning
         self.device = torch.device(device)
         self.world_size, self.rank = world_size, rank
+        self.checkpoint_format = checkpoint_format  # e.g. "ckpt_{epoch}.pt": saved after every epoch
         self._initialized = False
+        self._reduce_when_ready = False   # the image gradient of the running step triggers an update
+        self._pending = None              # in-flight asynchronous all_reduce of the image gradient
         self.epoch_losses, self.epoch_reg_terms = [], []
         self.iter_losses, self.iter_reg_terms = [], []
 
@@ -111,6 +122,7 @@ class LDDMMAtlasBuilder:
         with torch.no_grad():
             if need_image_grad:
                 self.I_grad_acc += grads[1]
+                self._image_grad_ready()
             norm_factor = img.shape[0] / self.num_subjects
             p = grads[0]
             if self.momentum_preconditioning:
@@ -118,13 +130,24 @@ class LDDMMAtlasBuilder:
             m = m.detach().add_(p, alpha=-self.learning_rate_pose)
         return m, (loss * norm_factor).detach(), (reg_term * norm_factor).detach()
 
+    def _image_grad_ready(self):
+        """Called as soon as the step's image gradient has been accumulated. When this iteration ends
+        with an image update, the NCCL all_reduce of the gradient (64 MiB at 256^3) starts here, on the
+        communicator's stream, and overlaps the momentum update (flat + axpy) that follows on the
+        compute stream; update_base_image() waits for it."""
+        if self._reduce_when_ready and self.world_size > 1 and self._pending is None:
+            self._pending = dist.all_reduce(self.I_grad_acc, async_op=True)
+
     def update_base_image(self, force=False):
         """Reference: lddmm.py:287-298 (all_reduce of the image gradient, average, SGD step)."""
         if (self.image_iters < self.image_update_freq and not force) or self.image_iters == 0:
             return
         with torch.no_grad():
             g = self.I_grad_acc
-            if self.world_size > 1:
+            if self._pending is not None:
+                self._pending.wait()
+                self._pending = None
+            elif self.world_size > 1:
                 dist.all_reduce(g)
             g /= self.image_iters * self.world_size
             self.I.add_(g, alpha=-self.learning_rate_image)
@@ -134,7 +157,11 @@ class LDDMMAtlasBuilder:
     def iteration(self, b):
         m, img = self.ms[b], self.images[self.batches[b]]
         for lit in range(self.lddmm_steps):
-            m, loss, reg_term = self.lddmm_step(m, img, need_image_grad=(lit == self.lddmm_steps - 1))
+            last = lit == self.lddmm_steps - 1
+            # will update_base_image() fire right after this iteration?
+            self._reduce_when_ready = last and self.image_iters + 1 >= self.image_update_freq
+            m, loss, reg_term = self.lddmm_step(m, img, need_image_grad=last)
+        self._reduce_when_ready = False
         self.ms[b] = m
         self.image_iters += 1
         self.update_base_image()
@@ -162,7 +189,37 @@ class LDDMMAtlasBuilder:
             l, r = self.epoch()
             self.epoch_losses.append(l)
             self.epoch_reg_terms.append(r)
+            if self.checkpoint_format is not None:
+                self.save(self.checkpoint_format.format(epoch=self._epoch))
         return self.I.detach(), self.ms
+
+    # ---- checkpoints ---------------------------------------------------------------------
+    # The reference writes one HDF5 file per rank (lddmm.py:238-285; h5py is not in this image): the
+    # same fields -- atlas, momenta concatenated over the rank's batches with their batch_sizes, and
+    # the four loss lists -- go through torch.save instead. Rank r > 0 appends ".rank<r>" to the name.
+    def _ckpt_name(self, filename):
+        return filename if self.rank == 0 else "%s.rank%d" % (filename, self.rank)
+
+    def save(self, filename):
+        self.initialize()
+        torch.save({
+            "atlas": self.I.detach().cpu(),
+            "momenta": torch.cat([m.detach().cpu() for m in self.ms]) if self.ms else None,
+            "batch_sizes": [int(m.shape[0]) for m in self.ms],
+            "epoch_losses": list(self.epoch_losses), "epoch_reg_terms": list(self.epoch_reg_terms),
+            "iter_losses": list(self.iter_losses), "iter_reg_terms": list(self.iter_reg_terms),
+        }, self._ckpt_name(filename))
+
+    def load(self, filename, load_image=True, load_momenta=True, load_losses=True):
+        """Restore state saved by save(); call before initialize() / run() (like lddmm.py:272-285)."""
+        f = torch.load(self._ckpt_name(filename), map_location="cpu")
+        if load_image:
+            self.I0 = f["atlas"]
+        if load_momenta and f["momenta"] is not None:
+            self.ms = list(torch.split(f["momenta"], f["batch_sizes"]))
+        if load_losses:
+            self.epoch_losses, self.epoch_reg_terms = list(f["epoch_losses"]), list(f["epoch_reg_terms"])
+            self.iter_losses, self.iter_reg_terms = list(f["iter_losses"]), list(f["iter_reg_terms"])
 
 
 def lddmm_atlas(dataset, **kwargs):

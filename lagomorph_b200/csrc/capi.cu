@@ -44,10 +44,6 @@ void count_launch(const char* name, cudaStream_t s) {
   }
 }
 bool debug_mode() { return g_debug.load(std::memory_order_relaxed) != 0; }
-int& rev_hint() {
-  static thread_local int r = 0;
-  return r;
-}
 
 // Launch-error check after enqueueing. In debug mode (the reference's
 // set_debug_mode, include/defs.h:15-23) also synchronise the stream, and unlike

@@ -11,10 +11,6 @@ int set_error(int code, const char* fmt, ...);
 int finish(cudaStream_t s, const char* what);  // checks launch error (+sync in debug mode)
 void count_launch(const char* name, cudaStream_t s);  // counts; in profile mode also timestamps
 bool debug_mode();
-// Traversal-direction hint for the next launches of the calling thread (0 = ascending block order,
-// 1 = descending). lgm_epdiff_step_fwd alternates it from kernel to kernel so that a kernel starts
-// with the part of its input its predecessor wrote last (still resident in the 126 MB L2).
-int& rev_hint();
 
 #define LGM_REQUIRE(cond, ...)                                   \
   do {                                                           \

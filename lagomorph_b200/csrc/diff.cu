@@ -558,16 +558,16 @@ extern "C" int lgm_ad_fwd(int dtype, void* out, const void* v, const void* w, in
   DISPATCH_RD(dtype, dim, ad_plain_t, out, v, w, N, shape, (cudaStream_t)stream);
 }
 namespace lgm {  // fp32 3-D fast paths (gather3.cu); LGM_EUNSUP = not applicable
-int Ad_star3_f32(void* out, const void* phi, const void* m, int64_t N, const int64_t* sh, cudaStream_t s);
+int Ad_star3_f32(void* out, const void* phi, const void* m, int64_t N, const int64_t* sh, int rev, cudaStream_t s);
 int compose3_f32(void* out, const void* u, const void* v, int64_t N, const int64_t* sh, double ds, double dt,
-                 cudaStream_t s);
+                 int rev, cudaStream_t s);
 }  // namespace lgm
 
 extern "C" int lgm_Ad_star_fwd(int dtype, void* out, const void* phiinv, const void* m, int64_t N,
                                int dim, const int64_t* shape, void* stream) {
   CHECK_N(N);
   if (dtype == LGM_F32 && dim == 3 && N > 0) {
-    int rc = Ad_star3_f32(out, phiinv, m, N, shape, (cudaStream_t)stream);
+    int rc = Ad_star3_f32(out, phiinv, m, N, shape, 0, (cudaStream_t)stream);
     if (rc != LGM_EUNSUP) return rc;
   }
   DISPATCH_RD(dtype, dim, Ad_star_generic, out, phiinv, m, N, shape, (cudaStream_t)stream);
@@ -576,7 +576,7 @@ extern "C" int lgm_compose_fwd(int dtype, void* out, const void* u, const void* 
                                int dim, const int64_t* shape, double ds, double dt, void* stream) {
   CHECK_N(N);
   if (dtype == LGM_F32 && dim == 3 && N > 0) {
-    int rc = compose3_f32(out, u, v, N, shape, ds, dt, (cudaStream_t)stream);
+    int rc = compose3_f32(out, u, v, N, shape, ds, dt, 0, (cudaStream_t)stream);
     if (rc != LGM_EUNSUP) return rc;
   }
   DISPATCH_RD(dtype, dim, compose_generic, out, u, v, N, shape, ds, dt, (cudaStream_t)stream);

@@ -10,6 +10,13 @@ namespace lgm {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// fp32 3-D fast paths (gather3.cu) and sharp with an explicit traversal direction (fluid.cu)
+int Ad_star3_f32(void* out, const void* phi, const void* m, int64_t N, const int64_t* sh, int rev, cudaStream_t s);
+int compose3_f32(void* out, const void* u, const void* v, int64_t N, const int64_t* sh, double ds, double dt,
+                 int rev, cudaStream_t s);
+int fluid_apply_dir(int dtype, void* out, const void* in, int64_t N, int dim, const int64_t* shape, int inverse,
+                    double alpha, double beta, double gamma, void* ws, int64_t ws_bytes, int rev, cudaStream_t s);
+
 template <typename R>
 __global__ void mul_mask_kernel(R* __restrict__ m, const R* __restrict__ mask, long long total,
                                 long long mask_total) {
@@ -63,16 +70,15 @@ extern "C" int lgm_epdiff_step_fwd(int dtype, void* phiinv_out, const void* phii
     const char* phi_g = (const char*)phiinv + n0 * sub;
     const char* m0_g = (const char*)m0 + n0 * sub;
     char* out_g = (char*)phiinv_out + n0 * sub;
-    // alternate the traversal direction from kernel to kernel (rev_hint, common.cuh): Ad_star and compose
-    // run in direction p, the slab passes of sharp in !p (its X pass in p again); p flips every step
-    // because compose(p) leaves the far end of phiinv in L2 for the next step's Ad_star.
-    static thread_local int parity = 0;
+    // traversal directions (explicit arguments, no state across calls): Ad_star and compose ascending,
+    // the slab passes of sharp descending (its X pass ascending again), so that each kernel starts on
+    // the data its predecessor wrote last (L2). lgm_expmap_fwd additionally flips all of them from
+    // step to step.
     static const bool alternate = getenv("LGM_NO_ALTERNATE") == nullptr;
-    const int p = alternate ? parity : 0;
-    if (n0 + G >= N) parity ^= 1;
-    rev_hint() = p;
-    int rc = lgm_Ad_star_fwd(dtype, m, phi_g, m0_g, g, dim, shape, stream);
-    if (rc) { rev_hint() = 0; return rc; }
+    int rc = LGM_EUNSUP;
+    if (dtype == LGM_F32 && dim == 3) rc = Ad_star3_f32(m, phi_g, m0_g, g, shape, 0, (cudaStream_t)stream);
+    if (rc == LGM_EUNSUP) rc = lgm_Ad_star_fwd(dtype, m, phi_g, m0_g, g, dim, shape, stream);
+    if (rc) return rc;
     if (mommask) {  // full-shape mask (N,dim,...), applied like `m = m * mommask` (lddmm.py:41-42)
       const long long total = g * dim * V;
       const char* mk = (const char*)mommask + n0 * sub;
@@ -82,12 +88,13 @@ extern "C" int lgm_epdiff_step_fwd(int dtype, void* phiinv_out, const void* phii
         mul_mask_kernel<double><<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((double*)m, (const double*)mk, total, total);
       count_launch("mul_mask", (cudaStream_t)stream);
     }
-    rev_hint() = alternate ? !p : 0;
-    rc = lgm_fluid_apply(dtype, m, m, g, dim, shape, 1, alpha, beta, gamma, ws, scratch_bytes - (int64_t)field, stream);
-    rev_hint() = p;
+    rc = fluid_apply_dir(dtype, m, m, g, dim, shape, 1, alpha, beta, gamma, ws, scratch_bytes - (int64_t)field,
+                         alternate ? 1 : 0, (cudaStream_t)stream);
+    if (rc) return rc;
     // compose_disp_vel(phiinv, v, -dt) = compose(v, phiinv, ds=-dt, dt=1)  (deform.py:58-62)
-    if (!rc) rc = lgm_compose_fwd(dtype, out_g, m, phi_g, g, dim, shape, -dt, 1.0, stream);
-    rev_hint() = 0;
+    rc = LGM_EUNSUP;
+    if (dtype == LGM_F32 && dim == 3) rc = compose3_f32(out_g, m, phi_g, g, shape, -dt, 1.0, 0, (cudaStream_t)stream);
+    if (rc == LGM_EUNSUP) rc = lgm_compose_fwd(dtype, out_g, m, phi_g, g, dim, shape, -dt, 1.0, stream);
     if (rc) return rc;
   }
   return LGM_OK;

@@ -1018,7 +1018,7 @@ struct FastLaunch {
   }
   template <int NX, int D, int NCH, bool INVERSE>
   static int xpass1(C* spec, long long N, long long plane, int Zc, const FluidPlan& p, double alpha,
-                    double beta, double gamma, R scale, cudaStream_t s) {
+                    double beta, double gamma, R scale, int rev, cudaStream_t s) {
     // tile width: 32 words (256 B runs) while the tile stays small, else the class default
     constexpr int TX = (sizeof(R) == 4 && NCH * NX <= LGM_XPASS_TX32_MAX) ? 32 : T;  // 32 at NX=256 measured slower (regs)
     const size_t smem = sizeof(C) * ((size_t)NCH * NX * TX + NX) + sizeof(R) * 2 * NX;
@@ -1026,19 +1026,19 @@ struct FastLaunch {
     dim3 grid((unsigned)cdiv(plane, TX), (unsigned)(NCH == 1 ? N * D : N));
     xpass2_kernel<R, NX, TX, D, NCH, INVERSE><<<grid, kFftThreads, smem, s>>>(
         spec, plane, Zc, (const C*)p.tw[0], (const R*)p.wl[0], (const R*)p.sl[0], (const R*)p.wl[1],
-        (const R*)p.sl[1], (const R*)p.wl[2], (const R*)p.sl[2], alpha, beta, gamma, scale, rev_hint());
+        (const R*)p.sl[1], (const R*)p.wl[2], (const R*)p.sl[2], alpha, beta, gamma, scale, rev);
     count_launch("xpass", s);
     return LGM_OK;
   }
   template <int NX, int D>
   static int xpass(C* spec, long long N, long long plane, int Zc, const FluidPlan& p, int inverse,
-                   double alpha, double beta, double gamma, R scale, cudaStream_t s) {
+                   double alpha, double beta, double gamma, R scale, int rev, cudaStream_t s) {
     if (beta == 0.0) {
-      return inverse ? xpass1<NX, D, 1, true>(spec, N, plane, Zc, p, alpha, beta, gamma, scale, s)
-                     : xpass1<NX, D, 1, false>(spec, N, plane, Zc, p, alpha, beta, gamma, scale, s);
+      return inverse ? xpass1<NX, D, 1, true>(spec, N, plane, Zc, p, alpha, beta, gamma, scale, rev, s)
+                     : xpass1<NX, D, 1, false>(spec, N, plane, Zc, p, alpha, beta, gamma, scale, rev, s);
     }
-    return inverse ? xpass1<NX, D, D, true>(spec, N, plane, Zc, p, alpha, beta, gamma, scale, s)
-                   : xpass1<NX, D, D, false>(spec, N, plane, Zc, p, alpha, beta, gamma, scale, s);
+    return inverse ? xpass1<NX, D, D, true>(spec, N, plane, Zc, p, alpha, beta, gamma, scale, rev, s)
+                   : xpass1<NX, D, D, false>(spec, N, plane, Zc, p, alpha, beta, gamma, scale, rev, s);
   }
 };
 
@@ -1069,23 +1069,23 @@ struct FastLaunch {
 // Slab path launchers (3-D, Y == Z in {16,32,64,128}); LGM_EUNSUP when the shape has no slab kernel.
 template <typename R, int YZ>
 static int slab_launch(bool inv, void* real, typename Cx<R>::T* spec, long long slabs, const FluidPlan& p,
-                       cudaStream_t s) {
+                       int rev, cudaStream_t s) {
   using C = typename Cx<R>::T;
   constexpr int M = YZ / 2;
   const size_t smem = sizeof(C) * ((size_t)(M + 1) * (YZ + 1) + YZ + M + YZ);
   if (!inv) {
     LGM_CUDA_TRY(set_smem(slab_fwd_kernel<R, YZ, YZ>, smem), "slab_fwd smem");
-    slab_fwd_kernel<R, YZ, YZ><<<(unsigned)slabs, kFftThreads, smem, s>>>(spec, (const R*)real, (const C*)p.tw[2], (const C*)p.tw[1], rev_hint());
+    slab_fwd_kernel<R, YZ, YZ><<<(unsigned)slabs, kFftThreads, smem, s>>>(spec, (const R*)real, (const C*)p.tw[2], (const C*)p.tw[1], rev);
     count_launch("slab_fwd", s);
   } else {
     LGM_CUDA_TRY(set_smem(slab_inv_kernel<R, YZ, YZ>, smem), "slab_inv smem");
-    slab_inv_kernel<R, YZ, YZ><<<(unsigned)slabs, kFftThreads, smem, s>>>((R*)real, spec, (const C*)p.tw[2], (const C*)p.tw[1], rev_hint());
+    slab_inv_kernel<R, YZ, YZ><<<(unsigned)slabs, kFftThreads, smem, s>>>((R*)real, spec, (const C*)p.tw[2], (const C*)p.tw[1], rev);
     count_launch("slab_inv", s);
   }
   return LGM_OK;
 }
 // 256 x 256 slabs (fp32): four-CTA cluster kernels, see cslab_fwd_kernel.
-static int cslab_launch(bool inv, void* real, float2* spec, long long slabs, const FluidPlan& p, cudaStream_t s) {
+static int cslab_launch(bool inv, void* real, float2* spec, long long slabs, const FluidPlan& p, int rev, cudaStream_t s) {
   // LGM_NO_CLUSTER_SLAB: kernel experiments. `broken` is set when the device refuses the cluster
   // launch (e.g. a partition without enough co-schedulable SMs): the unfused passes take over.
   static const bool off = getenv("LGM_NO_CLUSTER_SLAB") != nullptr;
@@ -1094,12 +1094,12 @@ static int cslab_launch(bool inv, void* real, float2* spec, long long slabs, con
   const size_t smem = sizeof(float2) * ((size_t)kCsRows * kCsP + 256 + 128 + 256);
   if (!inv) {
     if (set_smem(cslab_fwd_kernel, smem) != cudaSuccess) { cudaGetLastError(); broken = true; return LGM_EUNSUP; }
-    cslab_fwd_kernel<<<(unsigned)(kCsNC * slabs), kCsThreads, smem, s>>>(spec, (const float*)real, (const float2*)p.tw[2], (const float2*)p.tw[1], rev_hint());
+    cslab_fwd_kernel<<<(unsigned)(kCsNC * slabs), kCsThreads, smem, s>>>(spec, (const float*)real, (const float2*)p.tw[2], (const float2*)p.tw[1], rev);
     if (cudaPeekAtLastError() != cudaSuccess) { cudaGetLastError(); broken = true; return LGM_EUNSUP; }
     count_launch("slab_fwd", s);
   } else {
     if (set_smem(cslab_inv_kernel, smem) != cudaSuccess) { cudaGetLastError(); broken = true; return LGM_EUNSUP; }
-    cslab_inv_kernel<<<(unsigned)(kCsNC * slabs), kCsThreads, smem, s>>>((float*)real, spec, (const float2*)p.tw[2], (const float2*)p.tw[1], rev_hint());
+    cslab_inv_kernel<<<(unsigned)(kCsNC * slabs), kCsThreads, smem, s>>>((float*)real, spec, (const float2*)p.tw[2], (const float2*)p.tw[1], rev);
     if (cudaPeekAtLastError() != cudaSuccess) { cudaGetLastError(); broken = true; return LGM_EUNSUP; }
     count_launch("slab_inv", s);
   }
@@ -1108,16 +1108,16 @@ static int cslab_launch(bool inv, void* real, float2* spec, long long slabs, con
 
 template <typename R>
 static int slab_pass(bool inv, int Y, int Z, void* real, typename Cx<R>::T* spec, long long slabs,
-                     const FluidPlan& p, cudaStream_t s) {
+                     const FluidPlan& p, int rev, cudaStream_t s) {
   if (Y != Z) return LGM_EUNSUP;
   if constexpr (sizeof(R) == 4) {
-    if (Y == 256) return cslab_launch(inv, real, spec, slabs, p, s);
+    if (Y == 256) return cslab_launch(inv, real, spec, slabs, p, rev, s);
   }
   switch (Y) {
-    case 16: return slab_launch<R, 16>(inv, real, spec, slabs, p, s);
-    case 32: return slab_launch<R, 32>(inv, real, spec, slabs, p, s);
-    case 64: return slab_launch<R, 64>(inv, real, spec, slabs, p, s);
-    case 128: return slab_launch<R, 128>(inv, real, spec, slabs, p, s);
+    case 16: return slab_launch<R, 16>(inv, real, spec, slabs, p, rev, s);
+    case 32: return slab_launch<R, 32>(inv, real, spec, slabs, p, rev, s);
+    case 64: return slab_launch<R, 64>(inv, real, spec, slabs, p, rev, s);
+    case 128: return slab_launch<R, 128>(inv, real, spec, slabs, p, rev, s);
     default: return LGM_EUNSUP;
   }
 }
@@ -1143,7 +1143,9 @@ static long long chunk_budget_bytes() {
 template <typename R>
 static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64_t* shape,
                       int inverse, double alpha, double beta, double gamma, void* ws,
-                      const FluidPlan& p, cudaStream_t s) {
+                      const FluidPlan& p, int rev0, cudaStream_t s) {
+  // rev0: traversal direction of the two slab passes (0 = ascending block order); the X pass between
+  // them runs the other way round so that each pass starts on what its predecessor wrote last (L2)
   using C = typename Cx<R>::T;
   using FL = FastLaunch<R>;
   constexpr int MAXN = sizeof(R) == 4 ? 512 : 256;
@@ -1164,8 +1166,8 @@ static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64
     R* out_g = (R*)out + n0 * dim * V;
     const long long rows = g * dim * (V / nlast);
     int rc = LGM_EUNSUP;
-    const int rev0 = rev_hint();  // forward slab: as hinted; X pass: opposite; inverse slab: as hinted
-    if (dim == 3) rc = slab_pass<R>(false, Y, nlast, (void*)in_g, spec, g * dim * X, p, s);
+    const int revx = alternate_passes() ? !rev0 : rev0;
+    if (dim == 3) rc = slab_pass<R>(false, Y, nlast, (void*)in_g, spec, g * dim * X, p, rev0, s);
     const bool slab = (rc == LGM_OK);
     if (rc != LGM_OK && rc != LGM_EUNSUP) return rc;
     if (!slab) {
@@ -1180,9 +1182,7 @@ static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64
         if (rc) return rc;
       }
       rc = LGM_EUNSUP;
-      if (alternate_passes()) rev_hint() = !rev0;
-      LGM_SWITCH_POW2(X, MAXN, rc = (FL::template xpass<NN, 3>(spec, g, (long long)Y * Zc, Zc, p, inverse, alpha, beta, gamma, scale, s)));
-      rev_hint() = rev0;
+      LGM_SWITCH_POW2(X, MAXN, rc = (FL::template xpass<NN, 3>(spec, g, (long long)Y * Zc, Zc, p, inverse, alpha, beta, gamma, scale, revx, s)));
       if (rc) return rc;
       if (!slab) {
         rc = LGM_EUNSUP;
@@ -1191,12 +1191,12 @@ static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64
       }
     } else {
       rc = LGM_EUNSUP;
-      LGM_SWITCH_POW2(X, MAXN, rc = (FL::template xpass<NN, 2>(spec, g, (long long)Zc, Zc, p, inverse, alpha, beta, gamma, scale, s)));
+      LGM_SWITCH_POW2(X, MAXN, rc = (FL::template xpass<NN, 2>(spec, g, (long long)Zc, Zc, p, inverse, alpha, beta, gamma, scale, rev0, s)));
       if (rc) return rc;
     }
     rc = LGM_EUNSUP;
     if (slab) {
-      rc = slab_pass<R>(true, Y, nlast, (void*)out_g, spec, g * dim * X, p, s);
+      rc = slab_pass<R>(true, Y, nlast, (void*)out_g, spec, g * dim * X, p, rev0, s);
       if (rc == LGM_EUNSUP) {  // cluster launch refused after the forward slab ran: unfused inverse passes
         LGM_SWITCH_POW2(Y, MAXN, rc = (FL::template ypass<NN, true>(spec, (int)(g * dim), X, Zc, (const C*)p.tw[1], s)));
         if (rc) return rc;
@@ -1277,7 +1277,7 @@ static int64_t fluid_ws_bytes(int64_t N, int dim, const int64_t* shape) {
 
 template <typename R>
 int fluid_apply_t(void* out, const void* in, int64_t N, int dim, const int64_t* shape, int inverse,
-                  double alpha, double beta, double gamma, void* ws, int64_t ws_bytes,
+                  double alpha, double beta, double gamma, void* ws, int64_t ws_bytes, int rev,
                   cudaStream_t s) {
   if (N == 0) return LGM_OK;
   for (int a = 0; a < dim; ++a)
@@ -1291,7 +1291,7 @@ int fluid_apply_t(void* out, const void* in, int64_t N, int dim, const int64_t* 
   if (p->fast) {
     if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws) & 15)
       return set_error(LGM_EINVAL, "lgm_fluid_apply: pointers must be 16-byte aligned");
-    rc = fluid_fast<R>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, *p, s);
+    rc = fluid_fast<R>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, *p, rev, s);
   } else {
     rc = fluid_naive<R>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, *p, s);
   }
@@ -1299,8 +1299,21 @@ int fluid_apply_t(void* out, const void* in, int64_t N, int dim, const int64_t* 
   return finish(s, "lgm_fluid_apply");
 }
 
-template int fluid_apply_t<float>(void*, const void*, int64_t, int, const int64_t*, int, double, double, double, void*, int64_t, cudaStream_t);
-template int fluid_apply_t<double>(void*, const void*, int64_t, int, const int64_t*, int, double, double, double, void*, int64_t, cudaStream_t);
+template int fluid_apply_t<float>(void*, const void*, int64_t, int, const int64_t*, int, double, double, double, void*, int64_t, int, cudaStream_t);
+template int fluid_apply_t<double>(void*, const void*, int64_t, int, const int64_t*, int, double, double, double, void*, int64_t, int, cudaStream_t);
+
+// lgm_fluid_apply with an explicit traversal direction (used by the EPDiff step / shoot drivers)
+int fluid_apply_dir(int dtype, void* out, const void* in, int64_t N, int dim, const int64_t* shape, int inverse,
+                    double alpha, double beta, double gamma, void* ws, int64_t ws_bytes, int rev, cudaStream_t s) {
+  if (dim != 2 && dim != 3) return set_error(LGM_EINVAL, "Only two- and three-dimensional fluid metric is supported");
+  if (N < 0 || N > 21845) return set_error(LGM_EINVAL, "lgm_fluid_apply: batch size out of range");
+  if (!(dim == 2 ? geom_fits<2>(shape) : geom_fits<3>(shape))) return set_error(LGM_EINVAL, "lgm_fluid_apply: volume too large");
+  if (dtype == LGM_F32)
+    return fluid_apply_t<float>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, ws_bytes, rev, s);
+  if (dtype == LGM_F64)
+    return fluid_apply_t<double>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, ws_bytes, rev, s);
+  return set_error(LGM_EINVAL, "lgm_fluid_apply: unsupported dtype %d", dtype);
+}
 
 int64_t fluid_workspace_bytes(int dtype, int64_t N, int dim, const int64_t* shape) {
   return dtype == LGM_F32 ? fluid_ws_bytes<float>(N, dim, shape) : fluid_ws_bytes<double>(N, dim, shape);
@@ -1318,14 +1331,8 @@ extern "C" int64_t lgm_fluid_workspace_bytes(int dtype, int64_t N, int dim, cons
 extern "C" int lgm_fluid_apply(int dtype, void* out, const void* in, int64_t N, int dim,
                                const int64_t* shape, int inverse, double alpha, double beta,
                                double gamma, void* workspace, int64_t workspace_bytes, void* stream) {
-  LGM_REQUIRE(dim == 2 || dim == 3, "Only two- and three-dimensional fluid metric is supported");
-  LGM_REQUIRE(N >= 0 && N <= 21845, "lgm_fluid_apply: batch size out of range");
-  LGM_REQUIRE(dim == 2 ? geom_fits<2>(shape) : geom_fits<3>(shape), "lgm_fluid_apply: volume too large");
-  if (dtype == LGM_F32)
-    return fluid_apply_t<float>(out, in, N, dim, shape, inverse, alpha, beta, gamma, workspace, workspace_bytes, (cudaStream_t)stream);
-  if (dtype == LGM_F64)
-    return fluid_apply_t<double>(out, in, N, dim, shape, inverse, alpha, beta, gamma, workspace, workspace_bytes, (cudaStream_t)stream);
-  return set_error(LGM_EINVAL, "lgm_fluid_apply: unsupported dtype %d", dtype);
+  return fluid_apply_dir(dtype, out, in, N, dim, shape, inverse, alpha, beta, gamma, workspace, workspace_bytes, 0,
+                         (cudaStream_t)stream);
 }
 
 template <typename R>

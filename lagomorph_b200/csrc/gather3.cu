@@ -55,7 +55,7 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
                int X, int Y, int Z, float dh, float dl, float dsr, float dtr, int rev) {
   // blockDim = (32, 8/BX, BX): BX neighbouring x slabs share a CTA so that the upper-x corner rows
   // of one slab are the lower-x rows of the next (L1 reuse instead of a second L2 fetch)
-  // rev: walk the grid from its far end (see rev_hint() in common.cuh)
+  // rev: walk the grid from its far end (the EPDiff drivers alternate it from kernel to kernel)
   const unsigned bz = rev ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
   const unsigned by = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
   // a thread owns NR rows (j, j + 8/BX, ...) x NV chunks: NR * NV voxels, all centre loads up front
@@ -372,24 +372,24 @@ static bool fast3_ok(const void* p0, const void* p1, const void* p2, int64_t N, 
 }
 
 // returns LGM_EUNSUP when the fast path does not apply (caller falls back to the generic kernel)
-int Ad_star3_f32(void* out, const void* phi, const void* m, int64_t N, const int64_t* sh, cudaStream_t s) {
+int Ad_star3_f32(void* out, const void* phi, const void* m, int64_t N, const int64_t* sh, int rev, cudaStream_t s) {
   if (!fast3_ok(out, phi, m, N, sh)) return LGM_EUNSUP;
   constexpr int BX = LGM_GATHER_BX;
   dim3 grid((unsigned)cdiv(sh[2], 32 * LGM_GATHER_NV), (unsigned)cdiv(sh[1], (8 / BX) * LGM_GATHER_NR), (unsigned)(N * cdiv(sh[0], BX))), block(32, 8 / BX, BX);
   gather3_kernel<0, LGM_GATHER_NV, BX, LGM_GATHER_NR><<<grid, block, 0, s>>>((float*)out, (const float*)phi, (const float*)m, (int)sh[0],
-                                           (int)sh[1], (int)sh[2], 1.f, 0.f, 0.f, 0.f, rev_hint());
+                                           (int)sh[1], (int)sh[2], 1.f, 0.f, 0.f, 0.f, rev);
   count_launch("Ad_star", s);
   return finish(s, "lgm_Ad_star_fwd");
 }
 
 int compose3_f32(void* out, const void* u, const void* v, int64_t N, const int64_t* sh, double ds, double dt,
-                 cudaStream_t s) {
+                 int rev, cudaStream_t s) {
   if (!fast3_ok(out, u, v, N, sh)) return LGM_EUNSUP;
   const float dh = (float)ds, dl = (float)(ds - (double)dh);
   constexpr int BX = LGM_GATHER_BX;
   dim3 grid((unsigned)cdiv(sh[2], 32 * LGM_GATHER_NV), (unsigned)cdiv(sh[1], (8 / BX) * LGM_GATHER_NR), (unsigned)(N * cdiv(sh[0], BX))), block(32, 8 / BX, BX);
   gather3_kernel<1, LGM_GATHER_NV, BX, LGM_GATHER_NR><<<grid, block, 0, s>>>((float*)out, (const float*)u, (const float*)v, (int)sh[0],
-                                           (int)sh[1], (int)sh[2], dh, dl, (float)ds, (float)dt, rev_hint());
+                                           (int)sh[1], (int)sh[2], dh, dl, (float)ds, (float)dt, rev);
   count_launch("compose", s);
   return finish(s, "lgm_compose_fwd");
 }

@@ -25,9 +25,9 @@ struct Ax3 {
 // floor / fraction / clamped corner indices of one coordinate. Coordinates are first clamped to
 // +-2^22 voxels (far outside any volume: both corners are the border voxel there, and the result is
 // the border value for any weight), which lets floor() be a magic-number add with no slow path.
-__device__ __forceinline__ Ax3 axis_fast(float x, int n) {
+__device__ __forceinline__ Ax3 axis_fast(float x0, int n) {
   Ax3 a;
-  x = fminf(fmaxf(x, -4194304.f), 4194304.f);
+  float x = fminf(fmaxf(x0, -4194304.f), 4194304.f);
   float r = __fadd_rn(x, 12582912.f);  // 1.5 * 2^23: rounds x to an integer in the mantissa
   int f = __float_as_int(r) - 0x4B400000;
   float rf = __fsub_rn(r, 12582912.f);
@@ -35,7 +35,9 @@ __device__ __forceinline__ Ax3 axis_fast(float x, int n) {
     rf -= 1.f;
     f -= 1;
   }
-  a.t = x - rf;
+  // a NaN / Inf coordinate must give a NaN weight like the reference's t = x - floor(x) (the clamp above
+  // would turn it into a border sample): x0 * 0 is 0 for finite x0, NaN otherwise
+  a.t = __fmaf_rn(x0, 0.f, x - rf);
   a.i0 = min(max(f, 0), n - 1);
   a.i1 = min(max(f + 1, 0), n - 1);
   return a;
@@ -45,12 +47,12 @@ __device__ __forceinline__ Ax3 axis_fast(float x, int n) {
 // [-1, n - 1/2] (outside of it both corners are the border voxel and the result is the border value for
 // any weight, see z_pair()), floor() is ONE round-down add of the magic number, and the clamps of the
 // two corner indices shrink to one instruction each because floor is already in [-1, n-1].
-__device__ __forceinline__ Ax3 axis_fwd(float x, int n, float hi) {  // hi = n - 0.5f
+__device__ __forceinline__ Ax3 axis_fwd(float x0, int n, float hi) {  // hi = n - 0.5f
   Ax3 a;
-  x = fminf(fmaxf(x, -1.f), hi);
+  const float x = fminf(fmaxf(x0, -1.f), hi);
   const float r = __fadd_rd(x, 12582912.f);  // floor(x) + 1.5 * 2^23, exact
   const int f = __float_as_int(r) - 0x4B400000;
-  a.t = x - __fsub_rn(r, 12582912.f);
+  a.t = __fmaf_rn(x0, 0.f, x - __fsub_rn(r, 12582912.f));  // NaN / Inf coordinates stay NaN (see axis_fast)
   a.i0 = max(f, 0);
   a.i1 = min(f + 1, n - 1);
   return a;
@@ -99,7 +101,7 @@ __device__ __forceinline__ float trilerp(const float* __restrict__ img, unsigned
 __device__ __forceinline__ void z_pair(const Ax3& az, int Z, int& zs, float& v) {
   zs = min(az.i0, Z - 2);
   v = az.t;
-  if (az.i1 == az.i0) v = (az.i0 == 0) ? 0.f : 1.f;
+  if (az.i1 == az.i0) v = __fmaf_rn(az.t, 0.f, (az.i0 == 0) ? 0.f : 1.f);  // keeps a NaN weight NaN
 }
 
 // RN_f32(g * d) for a double d = dh + dl: stands in for the reference's "(float)((double)g * dt)"

@@ -51,9 +51,27 @@ def _fused_step(metric, m0, dt, phiinv, mommask, ws, out):
     return out
 
 
+def _fused_shoot(metric, m0, dt, num_steps, phiinv, mommask):
+    """The whole no-grad shoot as one library call (lgm_expmap_fwd); phiinv None = zeros."""
+    dev = m0.device
+    d, N, sh, code = L.spatial_dim(m0), m0.shape[0], L.shape_arr(m0.shape[2:]), L.dtype_code(m0)
+    alpha, beta, gamma = [float(p) for p in metric.params]
+    out = torch.empty_like(m0)
+    with torch.cuda.device(dev):
+        nbytes = int(L.lib.lgm_expmap_scratch_bytes(code, N, d, sh))
+        if nbytes < 0:
+            raise RuntimeError("lgm_expmap_scratch_bytes rejected the arguments")
+        buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        L.check(L.lib.lgm_expmap_fwd(code, L.ptr(out), L.ptr(phiinv), L.ptr(m0), L.ptr(mommask), N, d, sh, float(dt),
+                                     int(num_steps), alpha, beta, gamma, L.ptr(buf), nbytes, L.stream_ptr(dev)))
+    return out
+
+
 def _fusable(metric, m0, phiinv, mommask):
     if not isinstance(metric, FluidMetric) or _needs_grad(m0, phiinv, mommask):
         return False
+    if m0.dim() not in (4, 5) or m0.shape[1] != m0.dim() - 2:
+        return False  # the unfused chain raises "vector field is of wrong dimension" (adjrep._fused)
     if not (m0.is_cuda and phiinv.is_cuda and m0.shape == phiinv.shape and m0.dtype == phiinv.dtype):
         return False
     return mommask is None or (mommask.shape == m0.shape and mommask.dtype == m0.dtype and mommask.is_cuda)
@@ -210,18 +228,14 @@ def expmap(metric, m0, T=1.0, num_steps=10, phiinv=None, mommask=None, checkpoin
 
     checkpoints: False/None -> plain loop; int k -> recompute in blocks of k steps;
     True -> blocks of ~sqrt(num_steps) steps (num_steps unchanged, last block shorter)."""
-    if phiinv is None:
-        phiinv = torch.zeros_like(m0)
     dt = T / num_steps
     if checkpoints is None or checkpoints is False:
-        if _fusable(metric, m0, phiinv, mommask) and num_steps > 0:
-            m0c, cur = L.aligned(m0), L.aligned(phiinv)
+        if num_steps > 0 and _fusable(metric, m0, m0 if phiinv is None else phiinv, mommask):
             mk = None if mommask is None else mommask.contiguous()
-            ws = _StepWorkspace(m0c)
-            bufs = [torch.empty_like(cur), torch.empty_like(cur)]
-            for i in range(num_steps):
-                cur = _fused_step(metric, m0c, dt, cur, mk, ws, bufs[i % 2])
-            return cur
+            return _fused_shoot(metric, L.aligned(m0), dt, num_steps, None if phiinv is None else L.aligned(phiinv), mk)
+    if phiinv is None:
+        phiinv = torch.zeros_like(m0)
+    if checkpoints is None or checkpoints is False:
         if (num_steps > 0 and _needs_grad(m0, phiinv) and not _needs_grad(mommask)
                 and _fused_bwd_ok(metric, m0, phiinv, mommask)):
             return EPDiffShootFunction.apply(metric, m0, dt, num_steps, phiinv, mommask, True)

@@ -98,7 +98,11 @@ class FluidMetric(object):
                 torch.Tensor(np.sin(2.0 * np.pi * np.arange(Nf) / N)).type(dtype).to(device))
 
     def operator(self, mv, inverse):
-        return FluidMetricOperator.apply(self.params, None, inverse, mv)
+        # like the reference (metric.py:78), so that .luts / .shape / .complexshape are there for code
+        # that reads them; cached per (shape, dtype, device) and skipped under CUDA-graph capture
+        if mv.is_cuda and not torch.cuda.is_current_stream_capturing():
+            self.initialize_luts(shape=mv.shape, dtype=mv.dtype, device=mv.device)
+        return FluidMetricOperator.apply(self.params, self.luts, inverse, mv)
 
     def sharp(self, m):
         """Momentum -> velocity: apply the Green's function (reference: metric.py:81-88)."""

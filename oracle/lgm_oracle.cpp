@@ -21,6 +21,7 @@
 // Build: see oracle/Makefile (g++ -O2 -fopenmp -ffp-contract=off).
 
 #include <cmath>
+#include <vector>
 #include <cstddef>
 #include <cstdint>
 
@@ -654,6 +655,98 @@ void affine_fwd(R* out, const R* I, const R* A, const R* T, long N, long NI, lon
     }
 }
 
+// ---- affine_interp backward ------------------------------------------------------
+// cuda/affine.cu:171-328 (2-D), :330-536 (3-D), host :538-610. One block of 16 x 32 threads per
+// (n, c); thread (ii, jj) walks i = ii, ii+16, ..., j = jj, jj+32, ..., all k, accumulating its
+// partial sums of d_A / d_T in index order; the 512 partials are then tree-reduced by halving
+// (256, 128, ..., 1) with tid = ii*32 + jj, exactly the fp32 summation order of the reference.
+// d_I is the splat of grad_out (atomic, unordered); C > 1 adds the channels' block results.
+template <typename R>
+void affine_bwd(R* d_I, R* d_A, R* d_T, const R* go, const R* I, const R* A, const R* T, long N,
+                long NI, long C, int dim, const long* sh, int need_I, int need_A, int need_T) {
+  const int nx = sh[0], ny = sh[1], nz = dim == 3 ? sh[2] : 1;
+  const long V = (long)nx * ny * nz;
+  const bool bcast = (NI == 1 && N > 1);
+  const int BX = 16, BY = 32, NT = BX * BY;
+  const int nA = dim * dim;
+  if (need_I) for (long q = 0; q < NI * C * V; ++q) d_I[q] = 0;
+  if (need_A) for (long q = 0; q < N * nA; ++q) d_A[q] = 0;
+  if (need_T) for (long q = 0; q < N * dim; ++q) d_T[q] = 0;
+  const R ox = (R)(.5 * static_cast<R>(nx - 1));
+  const R oy = (R)(.5 * static_cast<R>(ny - 1));
+  const R oz = (R)(.5 * static_cast<R>(nz - 1));
+  for (long n = 0; n < N; ++n)
+    for (long c = 0; c < C; ++c) {
+      const R* gon = go + (n * C + c) * V;
+      const R* In = I + ((bcast ? 0 : n * C) + c) * V;
+      R* dIn = need_I ? d_I + ((bcast ? 0 : n * C) + c) * V : nullptr;
+      const R* An = A + n * nA;
+      const R* Tn = T + n * dim;
+      std::vector<R> part((size_t)NT * 12, R(0));  // [tid][0..8] = d_A partials, [9..11] = d_T
+#pragma omp parallel for collapse(2) schedule(static)
+      for (int ii = 0; ii < BX; ++ii)
+        for (int jj = 0; jj < BY; ++jj) {
+          R a[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+          for (int i = ii; i < nx; i += BX) {
+            R fi = static_cast<R>(i) - ox;
+            for (int j = jj; j < ny; j += BY) {
+              R fj = static_cast<R>(j) - oy;
+              if (dim == 2) {
+                long ix = (long)i * ny + j;
+                R hx = An[0] * fi + An[1] * fj + Tn[0] + ox;
+                R hy = An[2] * fi + An[3] * fj + Tn[1] + oy;
+                R diff = gon[ix];
+                if (need_I) splat2<R>(dIn, diff, hx, hy, nx, ny);
+                if (need_A || need_T) {
+                  R gx, gy;
+                  bilerp_grad<R>(gx, gy, In, hx, hy, nx, ny);
+                  gx *= diff;
+                  gy *= diff;
+                  if (need_A) {
+                    a[0] += gx * fi; a[1] += gx * fj;
+                    a[2] += gy * fi; a[3] += gy * fj;
+                  }
+                  if (need_T) { a[9] += gx; a[10] += gy; }
+                }
+              } else {
+                for (int k = 0; k < nz; ++k) {
+                  long ix = ((long)i * ny + j) * nz + k;
+                  R fk = static_cast<R>(k) - oz;
+                  R hx = An[0] * fi + An[1] * fj + An[2] * fk + Tn[0] + ox;
+                  R hy = An[3] * fi + An[4] * fj + An[5] * fk + Tn[1] + oy;
+                  R hz = An[6] * fi + An[7] * fj + An[8] * fk + Tn[2] + oz;
+                  R diff = gon[ix];
+                  if (need_I) splat3<R>(dIn, diff, hx, hy, hz, nx, ny, nz);
+                  if (need_A || need_T) {
+                    R gx, gy, gz;
+                    trilerp_grad<R>(gx, gy, gz, In, hx, hy, hz, nx, ny, nz);
+                    gx *= diff;
+                    gy *= diff;
+                    gz *= diff;
+                    if (need_A) {
+                      a[0] += gx * fi; a[1] += gx * fj; a[2] += gx * fk;
+                      a[3] += gy * fi; a[4] += gy * fj; a[5] += gy * fk;
+                      a[6] += gz * fi; a[7] += gz * fj; a[8] += gz * fk;
+                    }
+                    if (need_T) { a[9] += gx; a[10] += gy; a[11] += gz; }
+                  }
+                }
+              }
+            }
+          }
+          const int tid = ii * BY + jj;
+          for (int q = 0; q < 12; ++q) part[(size_t)tid * 12 + q] = a[q];
+        }
+      for (int h = NT / 2; h >= 1; h /= 2)
+        for (int tid = 0; tid < h; ++tid)
+          for (int q = 0; q < 12; ++q) part[(size_t)tid * 12 + q] += part[(size_t)(tid + h) * 12 + q];
+      if (need_A)
+        for (int q = 0; q < nA; ++q) d_A[n * nA + q] += part[q];   // C == 1: plain store; C > 1: atomicAdd
+      if (need_T)
+        for (int q = 0; q < dim; ++q) d_T[n * dim + q] += part[9 + q];
+    }
+}
+
 }  // namespace
 
 #define DISPATCH(dtype, CALL_F, CALL_D) \
@@ -732,6 +825,15 @@ void orc_affine_interp_fwd(int dtype, void* out, const void* I, const void* A, c
   DISPATCH(dtype,
            affine_fwd<float>((float*)out, (const float*)I, (const float*)A, (const float*)T, N, NI, C, dim, sh),
            affine_fwd<double>((double*)out, (const double*)I, (const double*)A, (const double*)T, N, NI, C, dim, sh));
+}
+void orc_affine_interp_bwd(int dtype, void* d_I, void* d_A, void* d_T, const void* go, const void* I,
+                           const void* A, const void* T, long N, long NI, long C, int dim, const long* sh,
+                           int need_I, int need_A, int need_T) {
+  DISPATCH(dtype,
+           affine_bwd<float>((float*)d_I, (float*)d_A, (float*)d_T, (const float*)go, (const float*)I,
+                             (const float*)A, (const float*)T, N, NI, C, dim, sh, need_I, need_A, need_T),
+           affine_bwd<double>((double*)d_I, (double*)d_A, (double*)d_T, (const double*)go, (const double*)I,
+                              (const double*)A, (const double*)T, N, NI, C, dim, sh, need_I, need_A, need_T));
 }
 
 }  // extern "C"

@@ -298,3 +298,186 @@ def sym(x, y, metric):
 
 def sym_dagger(x, y, metric):
     return ad_dagger(y, x, metric) - ad(x, y)
+
+
+# ---- autograd layer: the reference's torch.autograd.Functions over the oracle kernels -------------
+class InterpFn(torch.autograd.Function):  # deform.py:26-41
+    @staticmethod
+    def forward(ctx, I, u, dt):
+        ctx.dt = dt
+        ctx.save_for_backward(I, u)
+        return interp_forward(I, u, dt)
+
+    @staticmethod
+    def backward(ctx, go):
+        I, u = ctx.saved_tensors
+        d_I, d_u = interp_backward(go, I, u, ctx.dt, *ctx.needs_input_grad[:2])
+        return d_I, d_u, None
+
+
+class JtvfFn(torch.autograd.Function):  # diff.py:7-35
+    @staticmethod
+    def forward(ctx, v, w, displacement, transpose):
+        ctx.displacement, ctx.transpose = displacement, transpose
+        ctx.save_for_backward(v, w)
+        return jtvf_forward(v, w, displacement, transpose)
+
+    @staticmethod
+    def backward(ctx, go):
+        v, w = ctx.saved_tensors
+        d_v, d_w = jtvf_backward(go, v, w, ctx.displacement, ctx.transpose)
+        return d_v, d_w, None, None
+
+
+class FluidFn(torch.autograd.Function):  # metric.py:9-34: the backward is the same operator on gout
+    @staticmethod
+    def forward(ctx, metric, inverse, mv):
+        ctx.metric, ctx.inverse = metric, inverse
+        return metric.operator(mv, inverse)
+
+    @staticmethod
+    def backward(ctx, go):
+        return None, None, ctx.metric.operator(go, ctx.inverse)
+
+
+def ag_expmap(metric, m0, T=1.0, num_steps=10):
+    """differentiable expmap: lddmm.py:73-91 with Ad_star = adjrep.py:96-97, compose = deform.py:53-62"""
+    phiinv = torch.zeros_like(m0)
+    dt = T / num_steps
+    for i in range(num_steps):
+        m = JtvfFn.apply(phiinv, InterpFn.apply(m0, phiinv, 1.0), True, False)
+        v = FluidFn.apply(metric, True, m)
+        phiinv = (-dt) * v + 1.0 * InterpFn.apply(phiinv, v, -dt)
+    return phiinv
+
+
+def lddmm_step(metric, I, m, img, num_subjects, integration_steps=5, reg_weight=1e2, learning_rate_pose=2e2,
+               momentum_preconditioning=False, need_image_grad=True):
+    """One batch of LDDMMAtlasBuilder (lddmm.py:300-325, same-grid momenta). Returns
+    (new m, loss * norm_factor, reg_term * norm_factor, dL/dI or None)."""
+    m = m.detach().clone().requires_grad_(True)
+    I = I.detach().clone().requires_grad_(need_image_grad)
+    h = ag_expmap(metric, m, num_steps=integration_steps)
+    Idef = InterpFn.apply(I, h, 1.0)
+    v = FluidFn.apply(metric, True, m)
+    reg_term = reg_weight * (v * m).sum() / img.numel()
+    loss = ((Idef - img) ** 2).sum() / img.numel() + reg_term  # mse_loss(reduction="sum") / numel
+    loss.backward()
+    with torch.no_grad():
+        norm_factor = img.shape[0] / num_subjects
+        p = m.grad
+        if momentum_preconditioning:
+            p = metric.flat(p)
+        m_new = m.detach() - learning_rate_pose * p  # m.add_(-lr, p)
+    return m_new, (loss * norm_factor).item(), (reg_term * norm_factor).item(), (I.grad if need_image_grad else None)
+
+
+def lddmm_epoch(metric, I, ms, batches, num_subjects, learning_rate_image=1e4, image_update_freq=0, world_size=1,
+                **step_kwargs):
+    """One epoch of one rank (lddmm.py:327-358) over in-memory batches, image update as
+    lddmm.py:287-298 (gradient averaged over image_iters * world_size, plain SGD). Returns
+    (new I, new ms, epoch loss, epoch reg term)."""
+    I = I.detach().clone()
+    acc = torch.zeros_like(I)
+    iters = 0
+    eloss = ereg = 0.0
+    new_ms = []
+
+    def update(force=False):
+        nonlocal I, acc, iters
+        if (iters < image_update_freq and not force) or iters == 0:
+            return
+        I = I - learning_rate_image * (acc / (iters * world_size))
+        acc = torch.zeros_like(I)
+        iters = 0
+
+    for m, img in zip(ms, batches):
+        m, l, r, gI = lddmm_step(metric, I, m, img, num_subjects, **step_kwargs)
+        acc += gI
+        new_ms.append(m)
+        eloss += l
+        ereg += r
+        iters += 1
+        update()
+    update(force=True)
+    return I, new_ms, eloss, ereg
+
+
+# ---- affine atlas (config 4's caller) ---------------------------------------------------------
+def affine_interp_backward(go, I, A, T, need_I=True, need_A=True, need_T=True):
+    """cuda/affine.cu:538-610 -> kernels :171-536"""
+    go, I, A, T = _c(go), _c(I), _c(A), _c(T)
+    d = I.dim() - 2
+    N = A.shape[0]
+    d_I, d_A, d_T = torch.zeros_like(I), torch.zeros_like(A), torch.zeros_like(T)
+    lib().orc_affine_interp_bwd(I_(_code(I)), _p(d_I), _p(d_A), _p(d_T), _p(go), _p(I), _p(A), _p(T), L(N),
+                                L(I.shape[0]), L(I.shape[1]), I_(d), _sh(I.shape[2:]), I_(int(need_I)),
+                                I_(int(need_A)), I_(int(need_T)))
+    return d_I, d_A, d_T
+
+
+class AffineFn(torch.autograd.Function):  # affine.py:11-36
+    @staticmethod
+    def forward(ctx, I, A, T):
+        ctx.save_for_backward(I, A, T)
+        return affine_interp_forward(I, A, T)
+
+    @staticmethod
+    def backward(ctx, go):
+        I, A, T = ctx.saved_tensors
+        return affine_interp_backward(go, I, A, T, *ctx.needs_input_grad)
+
+
+def affine_atlas_epoch(I, As, Ts, imgs, batch_size, num_subjects, image_update_freq=0, affine_steps=1,
+                       reg_weightA=0.0, reg_weightT=0.0, learning_rate_A=1e-3, learning_rate_T=1e-2,
+                       learning_rate_I=1e5, world_size=1):
+    """One epoch of one rank of affine_atlas (affine.py:345-405) over in-memory images. As holds
+    A minus the identity, like the reference. Returns (I, As, Ts, epoch loss, iteration losses)."""
+    I = I.detach().clone()
+    As, Ts = As.detach().clone(), Ts.detach().clone()
+    dim = Ts.shape[1]
+    eye = torch.eye(dim, dtype=I.dtype).view(1, dim, dim)
+    nvox = float(np.prod(I.shape[2:]))
+    acc = torch.zeros_like(I)
+    image_iters = 0
+    epoch_loss = 0.0
+    iter_losses = []
+
+    def image_step():
+        nonlocal I, acc, image_iters
+        I = I - learning_rate_I * (acc / (image_iters * world_size))  # SGD step, affine.py:385-392
+        acc = torch.zeros_like(I)
+        image_iters = 0
+
+    for b0 in range(0, imgs.shape[0], batch_size):
+        sl = slice(b0, min(b0 + batch_size, imgs.shape[0]))
+        img = imgs[sl]
+        A, T = As[sl].clone(), Ts[sl].clone()
+        for affit in range(affine_steps):
+            A = A.detach().requires_grad_(True)
+            T = T.detach().requires_grad_(True)
+            last = affit == affine_steps - 1
+            Iin = I.detach().clone().requires_grad_(last)
+            Idef = AffineFn.apply(Iin, A + eye, T)
+            regloss = 0.0
+            if reg_weightA > 0:
+                regloss = regloss + 0.5 * reg_weightA * torch.dot(A.reshape(-1), A.reshape(-1))
+            if reg_weightT > 0:
+                regloss = regloss + 0.5 * reg_weightT * torch.dot(T.reshape(-1), T.reshape(-1))
+            loss = (((Idef - img) ** 2).sum() * (1.0 / nvox) + regloss) / img.shape[0]
+            loss.backward()
+            with torch.no_grad():
+                li = loss.item() * (img.shape[0] / num_subjects)
+                iter_losses.append(li)
+                A = A.detach() - learning_rate_A * A.grad
+                T = T.detach() - learning_rate_T * T.grad
+                if last:
+                    acc += Iin.grad
+        image_iters += 1
+        if image_iters == image_update_freq:
+            image_step()
+        epoch_loss += li
+        As[sl], Ts[sl] = A, T
+    if image_iters > 0:
+        image_step()
+    return I, As, Ts, epoch_loss, iter_losses

@@ -20,52 +20,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from util import RefCuda, randn  # noqa: E402
-
-
-def luts(shape, dtype):  # lagomorph/metric.py:53-75
-    cshape = list(shape)
-    cshape[-1] = cshape[-1] // 2 + 1
-    cos, sin = [], []
-    for (Nf, N) in zip(cshape[2:], shape[2:]):
-        cos.append(torch.Tensor(2.0 * (1.0 - np.cos(2 * np.pi * np.arange(Nf) / N))).type(dtype).cuda())
-        sin.append(torch.Tensor(np.sin(2.0 * np.pi * np.arange(Nf) / N)).type(dtype).cuda())
-    return cos, sin
-
-
-class RefPipeline:
-    """The reference's Python layer on top of its own CUDA kernels."""
-
-    def __init__(self, rc, params):
-        self.rc, self.params = rc, params
-
-    def fluid(self, mv, inverse):  # metric.py:11-19
-        d = mv.dim() - 2
-        dims = tuple(range(2, 2 + d))
-        F = torch.view_as_real(torch.fft.rfftn(mv, dim=dims, norm="ortho")).contiguous()
-        cos, sin = luts(mv.shape, mv.dtype)
-        self.rc.fluid_operator(F, inverse, cos, sin, *self.params)
-        return torch.fft.irfftn(torch.view_as_complex(F), s=mv.shape[2:], dim=dims, norm="ortho")
-
-    def Ad_star(self, phiinv, m):  # adjrep.py:86-97
-        return self.rc.jtvf_fwd(phiinv, self.rc.interp_fwd(m, phiinv, 1.0), True, False)
-
-    def ad_star(self, v, m):  # adjrep.py:69-83
-        return self.rc.jtvf_fwd(v, m, False, True) - self.rc.jtvf_adj_fwd(m, v)
-
-    def compose(self, u, v, ds, dt):  # deform.py:53-55
-        return ds * u + dt * self.rc.interp_fwd(v, u, ds)
-
-    def step(self, m0, dt, phiinv):  # lddmm.py:39-44
-        m = self.Ad_star(phiinv, m0)
-        v = self.fluid(m, True)
-        return self.compose(v, phiinv, -dt, 1.0)
-
-    def expmap(self, m0, num_steps):  # lddmm.py:87-91
-        phiinv = torch.zeros_like(m0)
-        for _ in range(num_steps):
-            phiinv = self.step(m0, 1.0 / num_steps, phiinv)
-        return phiinv
+from util import RefCuda, RefPipeline, randn, ref_luts as luts  # noqa: E402
 
 
 def main(out):

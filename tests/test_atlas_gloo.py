@@ -61,7 +61,12 @@ def test_two_ranks_match_one(tmp_path):
     # Two ranks x batch 2 see, per iteration, the same 4 subjects as one rank x batch 4; the image
     # gradient is averaged over ranks (lddmm.py:294-295) and the per-subject momentum gradient scales
     # with 1/batch (loss / img.numel(), lddmm.py:313), hence the doubled pose learning rate.
-    single = _make_builder(1, 0, data, batch_size=4, lr_pose=1.0)
+    # (subjects are assigned in the reference's DistributedSampler order: seed-0 permutation, strided)
+    from lagomorph_b200.atlas import shard_indices
+    r0, r1 = shard_indices(8, 2, 0), shard_indices(8, 2, 1)
+    assert sorted(r0 + r1) == list(range(8)) and r0 != [0, 2, 4, 6]
+    perm = r0[0:2] + r1[0:2] + r0[2:4] + r1[2:4]
+    single = _make_builder(1, 0, data[perm], batch_size=4, lr_pose=1.0)
     I1, _ = single.run()
     out = str(tmp_path / "r0.pt")
     mp.spawn(_worker, args=(2, _free_port(), data, out), nprocs=2, join=True)
@@ -97,7 +102,7 @@ def _affine_worker(rank, world_size, port, data, As, Ts, out):
 @pytest.mark.timeout(300)
 def test_affine_atlas_two_ranks_match_one(tmp_path):
     """2 ranks x 4 subjects (batches of 2) == one process over the same subjects in DistributedSampler
-    order (rank 0: subjects 0,2,4,6; rank 1: 1,3,5,7): same atlas, poses and epoch losses. With
+    order (seed-0 permutation strided by rank, lddmm.py:163-178): same atlas, poses and epoch losses. With
     image_update_freq = 0 the single process averages the image gradient over its 4 batches, the two
     ranks over 2 batches each and then over the ranks: the same number."""
     from lagomorph_b200.affine_atlas import affine_atlas
@@ -105,7 +110,8 @@ def test_affine_atlas_two_ranks_match_one(tmp_path):
     S = 8
     data = torch.randn(S, 1, 6, 5)
     As, Ts = 0.1 * torch.randn(S, 2, 2), 0.3 * torch.randn(S, 2)
-    perm = [0, 2, 4, 6, 1, 3, 5, 7]
+    from lagomorph_b200.atlas import shard_indices
+    perm = shard_indices(S, 2, 0) + shard_indices(S, 2, 1)
     I1, A1, T1, el1, _ = affine_atlas(data[perm], As[perm].clone(), Ts[perm].clone(), **_AFF_KW)
     inv = torch.argsort(torch.tensor(perm))
     out = str(tmp_path / "aff.pt")
@@ -114,3 +120,24 @@ def test_affine_atlas_two_ranks_match_one(tmp_path):
     assert torch.allclose(r["I"], I1, atol=1e-6)
     assert torch.allclose(r["A"], A1[inv], atol=1e-6) and torch.allclose(r["T"], T1[inv], atol=1e-6)
     assert torch.allclose(torch.tensor(r["el"]), torch.tensor(el1), atol=1e-6)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    """save() after two epochs, load() into a fresh builder, continue: same atlas and losses as
+    three epochs in one go (fields of the reference's HDF5 checkpoint, lddmm.py:238-285)."""
+    torch.manual_seed(3)
+    data = torch.randn(6, 1, 6, 5)
+    full = _make_builder(1, 0, data)
+    full.num_epochs = 3
+    I3, ms3 = full.run()
+    a = _make_builder(1, 0, data)
+    a.num_epochs = 2
+    a.checkpoint_format = str(tmp_path / "ck_{epoch}.pt")
+    a.run()
+    b = _make_builder(1, 0, data)
+    b.num_epochs = 1
+    b.load(str(tmp_path / "ck_1.pt"))
+    Ib, msb = b.run()
+    assert torch.allclose(Ib, I3, atol=1e-7)
+    assert all(torch.allclose(x, y, atol=1e-7) for x, y in zip(msb, ms3))
+    assert len(b.epoch_losses) == 3 and abs(b.epoch_losses[-1] - full.epoch_losses[-1]) < 1e-7

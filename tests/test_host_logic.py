@@ -64,13 +64,18 @@ def test_metric_from_args(lm):
 def test_shard_indices():
     from lagomorph_b200.atlas import shard_indices
     assert shard_indices(8, 1, 0) == list(range(8))
-    assert shard_indices(8, 4, 1) == [1, 5]
-    # same as DistributedSampler(shuffle=False): pad by wrapping
+    assert shard_indices(8, 4, 1, shuffle=False) == [1, 5]
+    # the reference builds DistributedSampler(dataset, num_replicas, rank) with its defaults
+    # (lddmm.py:163-178, affine.py:309-312): shuffle=True, seed 0, epoch 0, pad by wrapping
     from torch.utils.data.distributed import DistributedSampler
     for n, w in ((10, 4), (64, 8), (7, 2)):
+        seen = []
         for r in range(w):
+            assert list(DistributedSampler(list(range(n)), num_replicas=w, rank=r)) == shard_indices(n, w, r)
             ds = DistributedSampler(list(range(n)), num_replicas=w, rank=r, shuffle=False)
-            assert list(ds) == shard_indices(n, w, r)
+            assert list(ds) == shard_indices(n, w, r, shuffle=False)
+            seen += shard_indices(n, w, r)
+        assert sorted(set(seen)) == list(range(n))
 
 
 def test_expmap_host_chunk_schedule(lm):

@@ -1,0 +1,86 @@
+"""lgm_expmap_fwd (the whole shoot as one library call) against the step loop it replaces
+(lgm_epdiff_step_fwd per step): identical bit for bit, for every dtype / dim, with and without an
+initial displacement and a momentum mask (reference: lagomorph/lddmm.py:73-91); and BASELINE
+config 1 on the GPU against the CPU oracle."""
+import pytest
+import torch
+
+from util import smooth_field, relerr
+
+pytestmark = pytest.mark.gpu
+
+PARAMS = [0.1, 0.0, 0.01]
+
+
+def _inputs(lm, N, sh, dtype, seed=5, vmax=3.0):
+    d = len(sh)
+    m0 = smooth_field((N, d) + sh, torch.float64, seed, amp=1.0, sigma=2.0).to(dtype).cuda()
+    metric = lm.FluidMetric(PARAMS)
+    m0 = m0 * (vmax / metric.sharp(m0).abs().max())
+    return metric, m0
+
+
+def _loop(lm, metric, m0, T, steps, phiinv, mommask):
+    p = torch.zeros_like(m0) if phiinv is None else phiinv
+    for _ in range(steps):
+        p = lm.EPDiff_step(metric, m0, T / steps, p, mommask=mommask)
+    return p
+
+
+@pytest.mark.parametrize("sh", [(16, 16, 16), (8, 16, 32), (32, 16, 64), (12, 10, 14), (128, 128)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("steps", [1, 2, 5])
+def test_shoot_equals_step_loop(lm, sh, dtype, steps):
+    metric, m0 = _inputs(lm, 2, sh, dtype)
+    ref = _loop(lm, metric, m0, 1.0, steps, None, None)
+    out = lm.expmap(metric, m0, T=1.0, num_steps=steps)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("sh", [(16, 16, 32), (12, 10, 14), (32, 32)])
+def test_shoot_initial_displacement_and_mask(lm, sh):
+    metric, m0 = _inputs(lm, 3, sh, torch.float32, seed=6)
+    d = len(sh)
+    phi0 = smooth_field((3, d) + sh, torch.float32, 7, amp=2.0, sigma=2.0).cuda()
+    mask = (torch.rand((3, d) + sh, generator=torch.Generator().manual_seed(3)) > 0.2).float().cuda()
+    for p0, mk in ((phi0, None), (None, mask), (phi0, mask)):
+        ref = _loop(lm, metric, m0, 0.7, 3, p0, mk)
+        out = lm.expmap(metric, m0, T=0.7, num_steps=3, phiinv=p0, mommask=mk)
+        assert torch.equal(out, ref)
+
+
+def test_shoot_border_flow(lm):
+    """momenta strong enough to push samples across the volume border (clamped corners)"""
+    metric, m0 = _inputs(lm, 1, (16, 32, 32), torch.float32, seed=8, vmax=40.0)
+    ref = _loop(lm, metric, m0, 1.0, 4, None, None)
+    out = lm.expmap(metric, m0, T=1.0, num_steps=4)
+    assert torch.isfinite(out).all() and torch.equal(out, ref)
+
+
+def test_shoot_vs_oracle_c1(lm, orc):
+    """BASELINE config 1 (2-D 128x128, batch 8, 10 steps): product on the GPU vs the CPU oracle."""
+    N, sh = 8, (128, 128)
+    m0 = smooth_field((N, 2) + sh, torch.float64, 11, amp=1.0, sigma=4.0)
+    om = orc.FluidMetric(PARAMS)
+    m0 = (m0 * (4.0 / om.sharp(m0).abs().max())).float()
+    ref = orc.expmap(om, m0, num_steps=10)
+    out = lm.expmap(lm.FluidMetric(PARAMS), m0.cuda(), num_steps=10)
+    assert relerr(out, ref) <= 1e-4
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_nonfinite_displacement_propagates(lm, axis):
+    """A diverged deformation (NaN / Inf displacement) must give NaN samples, as the reference's
+    t = x - floor(x) does (include/interp.h:64-92), in the fp32 3-D fast paths too -- not a finite
+    border value that would mask the blow-up."""
+    sh = (8, 16, 32)
+    g = torch.Generator().manual_seed(2)
+    I = torch.randn((1, 3) + sh, generator=g).cuda()
+    for bad in (float("nan"), float("inf")):
+        u = torch.zeros((1, 3) + sh, device="cuda")
+        u[0, axis, 3, 5, 7] = bad
+        out = lm.interp(I, u)
+        assert torch.isnan(out[0, :, 3, 5, 7]).all()
+        assert torch.isfinite(out).sum().item() == out.numel() - 3
+        assert torch.isnan(lm.compose(u, I)[0, :, 3, 5, 7]).all()
+        assert torch.isnan(lm.Ad_star(u, I)[0, :, 3, 5, 7]).all()

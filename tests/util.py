@@ -206,3 +206,80 @@ class RefCuda:
                                                    ctypes.c_long(I.shape[0]), ctypes.c_long(I.shape[1]), d,
                                                    self._sh(I.shape[2:])))
         return d_I, d_A, d_T
+
+
+def ref_luts(shape, dtype, device="cuda"):
+    """cos / sin LUTs exactly as lagomorph/metric.py:53-75 builds them (float64 numpy -> dtype)"""
+    cshape = list(shape)
+    cshape[-1] = cshape[-1] // 2 + 1
+    cos, sin = [], []
+    for (Nf, N) in zip(cshape[2:], shape[2:]):
+        cos.append(torch.Tensor(2.0 * (1.0 - np.cos(2 * np.pi * np.arange(Nf) / N))).type(dtype).to(device))
+        sin.append(torch.Tensor(np.sin(2.0 * np.pi * np.arange(Nf) / N)).type(dtype).to(device))
+    return cos, sin
+
+
+class RefPipeline:
+    """The reference's Python layer on top of its OWN CUDA kernels (RefCuda): FluidMetric
+    (lagomorph/metric.py:11-19, torch.rfft(normalized=True) == torch.fft.rfftn(norm="ortho") on cuFFT),
+    Ad_star (adjrep.py:86-97), ad_star (:69-83), compose (deform.py:53-55), EPDiff_step
+    (lddmm.py:39-44) and the expmap loop (:87-91). Checker / baseline only."""
+
+    def __init__(self, rc, params):
+        self.rc, self.params = rc, params
+        self._luts = {}
+
+    def fluid(self, mv, inverse):
+        d = mv.dim() - 2
+        dims = tuple(range(2, 2 + d))
+        F = torch.view_as_real(torch.fft.rfftn(mv, dim=dims, norm="ortho")).contiguous()
+        key = (tuple(mv.shape[2:]), mv.dtype)
+        if key not in self._luts:
+            self._luts[key] = ref_luts(mv.shape, mv.dtype)
+        cos, sin = self._luts[key]
+        self.rc.fluid_operator(F, inverse, cos, sin, *self.params)
+        return torch.fft.irfftn(torch.view_as_complex(F), s=mv.shape[2:], dim=dims, norm="ortho")
+
+    def Ad_star(self, phiinv, m):
+        return self.rc.jtvf_fwd(phiinv, self.rc.interp_fwd(m, phiinv, 1.0), True, False)
+
+    def ad_star(self, v, m):
+        return self.rc.jtvf_fwd(v, m, False, True) - self.rc.jtvf_adj_fwd(m, v)
+
+    def compose(self, u, v, ds, dt):
+        return ds * u + dt * self.rc.interp_fwd(v, u, ds)
+
+    def step(self, m0, dt, phiinv):
+        m = self.Ad_star(phiinv, m0)
+        v = self.fluid(m, True)
+        return self.compose(v, phiinv, -dt, 1.0)
+
+    def expmap(self, m0, num_steps, T=1.0):
+        phiinv = torch.zeros_like(m0)
+        for _ in range(num_steps):
+            phiinv = self.step(m0, T / num_steps, phiinv)
+        return phiinv
+
+
+def baseline_momenta(N, shape, sigma=4.0, vmax=4.0, seed=1, params=(0.1, 0.0, 0.01), device="cuda"):
+    """BASELINE.md section 4 momenta on the GPU: white noise low-passed by a separable Gaussian
+    (sigma voxels, periodic), scaled so that max|sharp(m0)| * T = vmax voxels."""
+    d = len(shape)
+    m = torch.randn((N, d) + tuple(shape), generator=gen(seed)).to(device)
+    dims = tuple(range(2, 2 + d))
+    F = torch.fft.rfftn(m, dim=dims)
+    for a, n in enumerate(shape):
+        nf = n // 2 + 1 if a == d - 1 else n
+        k = torch.fft.rfftfreq(n) if a == d - 1 else torch.fft.fftfreq(n)
+        g = torch.exp(-2.0 * (np.pi * sigma * k[:nf]) ** 2).to(device)
+        F = F * g.view([-1 if i == 2 + a else 1 for i in range(F.dim())])
+    m = torch.fft.irfftn(F, s=tuple(shape), dim=dims).contiguous()
+    # scale with the reference composition of sharp (cuFFT + the Fourier symbol computed in torch)
+    Fm = torch.fft.rfftn(m, dim=dims, norm="ortho")
+    lam = torch.full(Fm.shape[2:], params[2], device=device, dtype=torch.float64)
+    for a, n in enumerate(shape):
+        nf = n // 2 + 1 if a == d - 1 else n
+        w = 2.0 * (1.0 - torch.cos(2 * np.pi * torch.arange(nf, dtype=torch.float64) / n)).to(device)
+        lam = lam + params[0] * w.view([-1 if i == a else 1 for i in range(d)])
+    v = torch.fft.irfftn(Fm / (lam * lam).float(), s=tuple(shape), dim=dims, norm="ortho")
+    return m * (vmax / v.abs().max())
