@@ -12,6 +12,11 @@ synthetic momenta per GPU. Default workload is BASELINE.json configs[1] (C2: 3-D
   cpu_baseline: the CPU oracle (port of the reference; the reference has no CPU path for this,
            SURVEY.md F1) on a bounded sample, rank 0 / N=1 only
 
+  also   : c3_256 (the shoot at 256^3), c3_atlas (config 3: one atlas epoch per GPU with the NCCL
+           all_reduce of the atlas gradient inside the timed region -- at every N), and at N = 1
+           c2_fwd_bwd, c4_affine, c5_deep (configs 2 / 4 / 5 with autograd) and ref_cuda (the
+           reference's own CUDA kernels on this GPU, oracle/_ref/libref_cuda.so)
+
 `--impl reference` times that CPU port alone (all host threads) on the same metric/config.
 """
 import argparse
@@ -43,26 +48,55 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_momenta(N, shape, seed, device=None, scale_to=4.0):
-    """White noise low-passed by the metric itself, scaled so that max|sharp(m0)| = 4 voxels
-    (BASELINE.md section 4). Generated on the CPU (seeded), deterministic per rank."""
+def make_momenta(N, shape, seed, device=None, sigma=4.0):
+    """BASELINE.md section 4 momenta: seeded white noise (CPU generator, deterministic per rank)
+    low-passed by a separable periodic Gaussian of sigma = 4 voxels. The smoothing is input
+    generation, not the product: torch.fft on `device` (or on the CPU when device is None).
+    The caller scales the result so that max|sharp(m0)| = 4 voxels."""
+    import math
     import torch
     g = torch.Generator().manual_seed(seed)
-    m = torch.randn((N, 3) + tuple(shape), generator=g, dtype=torch.float32)
-    return m
+    d = len(shape)
+    out = []
+    for n in range(N):                      # one subject at a time bounds the FFT workspace
+        m = torch.randn((1, d) + tuple(shape), generator=g, dtype=torch.float32)
+        if device is not None:
+            m = m.to(device)
+        dims = tuple(range(2, 2 + d))
+        F = torch.fft.rfftn(m, dim=dims)
+        for a, n_a in enumerate(shape):
+            k = torch.fft.rfftfreq(n_a) if a == d - 1 else torch.fft.fftfreq(n_a)
+            w = torch.exp(-2.0 * (math.pi * sigma * k) ** 2).to(F.device)
+            F = F * w.view([-1 if i == 2 + a else 1 for i in range(F.dim())])
+        out.append(torch.fft.irfftn(F, s=tuple(shape), dim=dims))
+    return torch.cat(out).contiguous()
+
+
+def gpu_numa_node(index):
+    """(node, why): the NUMA node the GPU hangs off, or (None, reason)"""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        path = "/sys/bus/pci/devices/%s/numa_node" % bus
+        if not os.path.exists(path):
+            return None, "no %s" % path
+        node = int(open(path).read())
+        if node < 0:
+            return None, "sysfs reports numa_node = %d for %s (single-node box or virtualised topology)" % (node, bus)
+        return node, None
+    except Exception as e:
+        return None, "%s: %s" % (type(e).__name__, e)
 
 
 def bind_to_gpu_numa_node(index):
     """Pin this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers
     are allocated (first touch places them on that node): with 8 ranks copying at once the
-    host<->device path, not the GPU, bounds the e2e number. Best effort: returns the node or None."""
+    host<->device path, not the GPU, bounds the e2e number. Returns (node or None, reason)."""
+    node, why = gpu_numa_node(index)
+    if node is None:
+        return None, why
     try:
-        import torch
-        p = torch.cuda.get_device_properties(index)
-        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
-        if node < 0:
-            return None
         cpus = set()
         for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
             a, _, b = part.partition("-")
@@ -70,10 +104,10 @@ def bind_to_gpu_numa_node(index):
         cpus &= os.sched_getaffinity(0)
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return node
-    except Exception:
-        pass
-    return None
+            return node, None
+        return None, "node %d has no CPU in this process's affinity mask" % node
+    except Exception as e:
+        return None, "%s: %s" % (type(e).__name__, e)
 
 
 class ClockSampler:
@@ -114,6 +148,179 @@ class ClockSampler:
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
+
+
+
+# ---- secondary workloads ("also") ---------------------------------------------------------------
+FWD_BWD_BYTES_PER_VOXEL_STEP = 324  # 96 forward + 228 backward (estimate), fp32 3-D
+
+
+def _timed(torch, fn, K, W, barrier, reduce_max):
+    for _ in range(W):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        fn()
+    e1.record()
+    barrier()
+    return reduce_max(e0.elapsed_time(e1)) / K
+
+
+def _blob_dataset(torch, S, n, dev, seed0=100):
+    """S synthetic subjects (1, n, n, n): one Gaussian blob each, centre jittered per subject;
+    generated lazily on the device so that a rank only materialises its own shard."""
+    ax = torch.arange(n, dtype=torch.float32, device=dev)
+
+    class Synth:
+        def __len__(self):
+            return S
+
+        def __getitem__(self, i):
+            g = torch.Generator().manual_seed(seed0 + int(i))
+            c = (n - 1) / 2 + (torch.rand(3, generator=g) - 0.5) * n / 8
+            e = [torch.exp(-((ax - float(c[d])) ** 2) / (2 * (n / 6) ** 2)) for d in range(3)]
+            return (e[0][:, None, None] * e[1][None, :, None] * e[2][None, None, :]).unsqueeze(0)
+
+    return Synth()
+
+
+def bench_c3_atlas(torch, dist, lm, dev, world, rank, hbm, barrier, reduce_max, K=2, W=1, n=256, per_gpu=8):
+    """BASELINE config 3: one atlas epoch (lagomorph/lddmm.py:287-358) over this rank's 8 subjects of
+    256^3 in one batch: 5-step expmap, deform, loss, backward through the shoot, momentum update, and
+    the image update with the NCCL all_reduce of the 64 MiB atlas gradient (+ one 2-scalar all_reduce
+    of the losses) INSIDE the timed region."""
+    S = per_gpu * world
+    b = lm.LDDMMAtlasBuilder(_blob_dataset(torch, S, n, dev), num_epochs=1, batch_size=per_gpu,
+                             lddmm_integration_steps=5, reg_weight=1e-2, learning_rate_pose=1.0,
+                             learning_rate_image=0.1, device=dev, world_size=world, rank=rank)
+    b.initialize()
+    n0 = lm.launch_count()
+    ms = _timed(torch, b.epoch, K, W, barrier, reduce_max)
+    launches = (lm.launch_count() - n0) // (K + W)
+    vs = S * n ** 3 * 5 / (ms * 1e-3)
+    out = {"value": S / (ms * 1e-3), "unit": "subjects/s", "ms_per_epoch": ms, "n_gpus": world,
+           "voxel_steps_per_s_fwd_bwd": vs,
+           "hbm_roofline_frac_324B": vs / world * FWD_BWD_BYTES_PER_VOXEL_STEP / 1e9 / hbm,
+           "collective": "NCCL all_reduce of the %d MiB atlas gradient (async, overlapping the momentum update) "
+                         "+ one all_reduce of 2 scalars, inside the timed region" % (n ** 3 * 4 >> 20) if world > 1
+                         else "none (1 rank)",
+           "gpu_launches_per_epoch": launches, "last_epoch_loss": b.iter_losses[-1] if b.iter_losses else None,
+           "config": {"shape": [n, n, n], "subjects": S, "subjects_per_gpu": per_gpu, "batch": per_gpu,
+                      "epdiff_steps": 5}}
+    del b
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_c2_fwd_bwd(torch, lm, dev, hbm, metric, barrier, reduce_max, K=3, W=1, n=128, batch=16, steps=10):
+    """BASELINE config 2, second figure: one pairwise-registration iteration = lddmm_step
+    (lagomorph/lddmm.py:300-325) with the image held fixed: shoot, deform, loss, full backward,
+    momentum update."""
+    data = _blob_dataset(torch, batch, n, dev, seed0=300)
+    b = lm.LDDMMAtlasBuilder(data, num_epochs=1, batch_size=batch, lddmm_integration_steps=steps, reg_weight=1e-2,
+                             learning_rate_pose=1.0, learning_rate_image=0.0, device=dev, metric=metric)
+    b.initialize()
+    m = make_momenta(batch, (n, n, n), 7, device=dev)
+    m.mul_(4.0 / metric.sharp(m).abs().max().item())
+    img = b.images[b.batches[0]]
+
+    def it():
+        b.lddmm_step(m, img, need_image_grad=False)
+
+    ms = _timed(torch, it, K, W, barrier, reduce_max)
+    vs = batch * n ** 3 * steps / (ms * 1e-3)
+    del b
+    torch.cuda.empty_cache()
+    return {"value": vs, "unit": "voxel-steps/s fwd+bwd", "ms_per_iteration": ms,
+            "hbm_roofline_frac_324B": vs * FWD_BWD_BYTES_PER_VOXEL_STEP / 1e9 / hbm,
+            "config": {"shape": [n, n, n], "batch": batch, "epdiff_steps": steps}}
+
+
+def bench_c4_affine(torch, lm, dev, hbm, barrier, reduce_max, K=5, W=2, n=192, batch=32):
+    """BASELINE config 4: affine_interp forward + backward with all three gradients (d_I, d_A, d_T)."""
+    g = torch.Generator(device=dev).manual_seed(1)
+    data = _blob_dataset(torch, batch, n, dev, seed0=500)
+    I = torch.stack([data[i] for i in range(batch)]).requires_grad_(True)
+    A = (torch.eye(3, device=dev)[None] + 0.05 * torch.randn((batch, 3, 3), device=dev, generator=g)).requires_grad_(True)
+    T = (2 * torch.randn((batch, 3), device=dev, generator=g)).requires_grad_(True)
+    go = torch.randn((batch, 1, n, n, n), device=dev, generator=g)
+    fwd_ms = _timed(torch, lambda: lm.affine_interp(I, A, T), K, W, barrier, reduce_max)
+
+    def both():
+        out = lm.affine_interp(I, A, T)
+        torch.autograd.grad(out, [I, A, T], go)
+
+    ms = _timed(torch, both, K, W, barrier, reduce_max)
+    vox = batch * n ** 3
+    return {"value": vox / (ms * 1e-3), "unit": "voxels/s fwd+bwd", "ms_fwd": fwd_ms, "ms_fwd_bwd": ms,
+            "fwd_frac_of_hbm_8B": vox * 8 / (fwd_ms * 1e-3) / 1e9 / hbm,
+            "bwd_frac_of_hbm_16B": vox * 16 / ((ms - fwd_ms) * 1e-3) / 1e9 / hbm,
+            "config": {"shape": [n, n, n], "batch": batch}}
+
+
+def bench_c5_deep(torch, lm, dev, hbm, metric, barrier, reduce_max, K=3, W=1, n=128, batch=4, steps=5):
+    """BASELINE config 5 (deep LDDMM): a small 3-D CNN (3 conv layers, 16 channels; cuDNN, a library,
+    timed separately) predicts the momenta (4, 3, 128^3) from the (atlas, subject) pair; the loss goes
+    through expmap, interp and the metric and loss.backward() reaches the CNN weights."""
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Conv3d(2, 16, 3, padding=1), torch.nn.ReLU(),
+                              torch.nn.Conv3d(16, 16, 3, padding=1), torch.nn.ReLU(),
+                              torch.nn.Conv3d(16, 3, 3, padding=1)).to(dev)
+    data = _blob_dataset(torch, batch + 1, n, dev, seed0=700)
+    J = torch.stack([data[i] for i in range(batch)])
+    I = data[batch].unsqueeze(0)
+    x = torch.cat([I.expand(batch, -1, -1, -1, -1), J], dim=1).contiguous()
+    with torch.no_grad():  # scale the (random-init) net's output to a flow of ~2 voxels
+        gain = 2.0 / metric.sharp(net(x)).abs().max().item()
+
+    def cnn_only():
+        m = net(x) * gain
+        m.backward(torch.ones_like(m))
+        net.zero_grad(set_to_none=True)
+
+    def full():
+        m = net(x) * gain
+        h = lm.expmap(metric, m, num_steps=steps)
+        Idef = lm.interp(I, h)
+        v = metric.sharp(m)
+        loss = ((Idef - J) ** 2).sum() / J.numel() + 1e-2 * (v * m).sum() / J.numel()
+        loss.backward()
+        net.zero_grad(set_to_none=True)
+
+    cnn_ms = _timed(torch, cnn_only, K, W, barrier, reduce_max)
+    ms = _timed(torch, full, K, W, barrier, reduce_max)
+    vs = batch * n ** 3 * steps / ((ms - cnn_ms) * 1e-3)
+    del net
+    torch.cuda.empty_cache()
+    return {"value": vs, "unit": "voxel-steps/s fwd+bwd (CNN time excluded)", "ms_total": ms, "ms_cnn_fwd_bwd": cnn_ms,
+            "hbm_roofline_frac_324B": vs * FWD_BWD_BYTES_PER_VOXEL_STEP / 1e9 / hbm,
+            "config": {"shape": [n, n, n], "batch": batch, "epdiff_steps": steps, "cnn": "3 x Conv3d(3^3), 16 ch (cuDNN)"}}
+
+
+def bench_ref_cuda(torch, metric, lm, dev, n=128, batch=2, steps=10):
+    """The reference's OWN CUDA kernels on this GPU: lagomorph/extension/cuda/*.cu compiled unmodified
+    for sm_100a against an ATen stand-in (oracle/_ref/libref_cuda.so) under the reference's Python
+    composition with cuFFT for torch.rfft (tests/util.py RefPipeline). Checker-side baseline."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import RefCuda, RefPipeline
+    if not RefCuda.available():
+        return {"unavailable": "oracle/_ref/libref_cuda.so not built (needs /root/reference at build time)"}
+    ref = RefPipeline(RefCuda(), PARAMS)
+    m0 = make_momenta(batch, (n, n, n), 1, device=dev)
+    m0.mul_(4.0 / metric.sharp(m0).abs().max().item())
+    ref.expmap(m0, 1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    want = ref.expmap(m0, steps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    got = lm.expmap(metric, m0, num_steps=steps)
+    err = ((got - want).abs().max() / want.abs().max()).item()
+    return {"value": batch * n ** 3 * steps / dt, "unit": "voxel-steps/s", "kind": "reference kernels, ATen shim",
+            "ms_per_shoot": dt * 1e3, "sample": "%d subjects of %d^3, %d EPDiff steps" % (batch, n, steps),
+            "product_vs_reference_max_rel_err": err}
 
 
 def cpu_port_throughput(shape, batch, steps, reps=1):
@@ -199,8 +406,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    numa, numa_why = bind_to_gpu_numa_node(local_rank) if world > 1 else (None, "single rank: not bound")
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "INFO")          # communicator / topology lines on stderr
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1
 
@@ -214,13 +423,12 @@ def main():
     def measure(workload, K, W, with_e2e=True):
         batch, shape, nsteps = WORKLOADS[workload]
         V = shape[0] * shape[1] * shape[2]
-        m_host = make_momenta(batch, shape, 1 + rank).pin_memory()
-        m0 = m_host.to(dev, non_blocking=True)
-        torch.cuda.synchronize()
+        m0 = make_momenta(batch, shape, 1 + rank, device=dev)
         # scale so the flow moves ~4 voxels (diffeomorphic, realistic gather locality)
-        v0max = metric.sharp(m0).abs().max().item()
-        m0.mul_(4.0 / v0max)
-        m_host.mul_(4.0 / v0max)
+        m0.mul_(4.0 / metric.sharp(m0).abs().max().item())
+        m_host = torch.empty(m0.shape, dtype=m0.dtype).pin_memory()
+        m_host.copy_(m0)
+        torch.cuda.synchronize()
         shoot = lambda: lm.expmap(metric, m0, num_steps=nsteps)
         sampler = ClockSampler(local_rank)
         sampler.start()  # runs through warm-up (same workload) and the timed region
@@ -328,18 +536,39 @@ def main():
                     "peak_source": peak_src, "algorithmic_bytes_per_voxel": alg_bytes(dom, shape)}
     step_frac = main_res["value"] / world * ALG_BYTES_PER_VOXEL_STEP / 1e9 / hbm
 
-    extra = None
-    if not args.no_extra and args.workload == "c2":
+    def reduce_max(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    extra = {}
+
+    def also(name, fn):  # never lose the main line
         try:
+            extra[name] = fn()
+        except Exception as e:
+            extra[name] = {"error": ("%s: %s" % (type(e).__name__, e))[:300]}
+            torch.cuda.empty_cache()
+
+    if not args.no_extra and args.workload == "c2":
+        def c3_shoot():
             r3 = measure("c3", max(2, args.steps // 2), 2, with_e2e=False)
-            extra = {"c3_256": {"value": r3["value"], "unit": "voxel-steps/s", "ms_per_step": r3["ms_per_step"],
-                                "hbm_roofline_frac_96B": r3["value"] / world * ALG_BYTES_PER_VOXEL_STEP / 1e9 / hbm,
-                                "config": {"shape": list(r3["shape"]), "batch_per_gpu": r3["batch"], "epdiff_steps": r3["nsteps"]}}}
-        except Exception as e:  # never lose the main line
-            extra = {"c3_256": {"error": str(e)[:200]}}
+            return {"value": r3["value"], "unit": "voxel-steps/s", "ms_per_step": r3["ms_per_step"],
+                    "hbm_roofline_frac_96B": r3["value"] / world * ALG_BYTES_PER_VOXEL_STEP / 1e9 / hbm,
+                    "kernel_ms_per_epdiff_step": {k: v["ms"] / (r3["kernel_reps"] * r3["nsteps"]) for k, v in r3["kernels"].items()},
+                    "config": {"shape": list(r3["shape"]), "batch_per_gpu": r3["batch"], "epdiff_steps": r3["nsteps"]}}
+        also("c3_256", c3_shoot)
+        also("c3_atlas", lambda: bench_c3_atlas(torch, dist, lm, dev, world, rank, hbm, barrier, reduce_max))
+        if world == 1:
+            also("c2_fwd_bwd", lambda: bench_c2_fwd_bwd(torch, lm, dev, hbm, metric, barrier, reduce_max))
+            also("c4_affine", lambda: bench_c4_affine(torch, lm, dev, hbm, barrier, reduce_max))
+            also("c5_deep", lambda: bench_c5_deep(torch, lm, dev, hbm, metric, barrier, reduce_max))
+            also("ref_cuda", lambda: bench_ref_cuda(torch, metric, lm, dev))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
         val, secs = cpu_port_throughput(shape, 2, nsteps)
         cpu = {"value": val, "unit": "voxel-steps/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "2 subjects of %dx%dx%d, %d EPDiff steps (%.1f s)" % (tuple(shape) + (nsteps, secs))}
@@ -353,7 +582,8 @@ def main():
                        "epdiff_steps": nsteps, "metric_params": PARAMS,
                        "l2": "inputs larger than L2 (%d MiB per field vs 126 MB)" % (batch * 3 * V * 4 >> 20),
                        "parallelism": "subjects sharded over ranks, no data-path collective",
-                       "host_numa_node": numa},
+                       "host_numa_node": numa, "host_numa_note": numa_why,
+                       "momenta": "white noise low-passed by a sigma=4 Gaussian, max|sharp(m0)| = 4 voxels (BASELINE.md 4)"},
             "hbm_roofline_frac_96B": step_frac,
             "roofline": roofline, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
             "e2e": main_res.get("e2e"), "gpu_launches": main_res["launches"], "clocks": main_res["clocks"],

@@ -256,15 +256,18 @@ def expmap(metric, m0, T=1.0, num_steps=10, phiinv=None, mommask=None, checkpoin
     return phiinv
 
 
-def _auto_chunks(N, num_steps=10, cap=5):
+def _auto_chunks(N, num_steps=10, cap=5, ratio=None):
     """Chunk sizes for expmap_host. Every chunk costs a fixed ~0.25 ms of launch tails, so chunks
     should be few and large; but the first host->device copy and the last device->host copy are
-    exposed, and a chunk's copy has to hide behind its neighbour's compute. With r = copy time /
-    compute time per subject (12 B per voxel over ~55 GB/s of PCIe 5 x16 against ~22 G voxel-steps/s:
-    r = 4.8 / num_steps) the sizes may grow by 1/r per chunk from 1 at the head, shrink to 1 at the
-    tail, and are capped in the middle: N = 16, 10 steps -> [1, 2, 4, 5, 3, 1]; 5 steps at any N
-    (copy as slow as compute) -> single subjects."""
-    g = max(1.0, num_steps / 4.8)
+    exposed, and a chunk's copy has to hide behind its neighbour's compute. With ratio r = copy time /
+    compute time per subject the sizes may grow by 1/r per chunk from 1 at the head, shrink to 1 at
+    the tail, and are capped in the middle: r = 0.48 (N = 16, 10 steps on a PCIe 5 x16 B200) ->
+    [1, 2, 4, 5, 3, 1]; r >= 1 (copy as slow as compute) -> single subjects.
+    expmap_host MEASURES r on this box (_copy_compute_ratio); ratio=None falls back to the figure of
+    the development box (12 B per voxel over ~55 GB/s against ~22 G voxel-steps/s: 4.8 / num_steps)."""
+    if ratio is None:
+        ratio = 4.8 / num_steps
+    g = max(1.0, 1.0 / max(ratio, 1e-3))
     head, tail = [], []
     h, t, left = 1.0, 1.0, N
     while left > 0:
@@ -309,7 +312,7 @@ def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chu
         return out
     # chunk: "auto", an int (uniform chunks) or a list of chunk sizes.
     if isinstance(chunk, str):
-        sizes = _auto_chunks(N, num_steps)
+        sizes = _auto_chunks(N, num_steps, ratio=_copy_compute_ratio(metric, m0_host, T, num_steps, dev))
     elif isinstance(chunk, (list, tuple)):
         sizes = [int(c) for c in chunk if int(c) > 0]
         assert sum(sizes) == N, "chunk sizes must add up to the batch"
@@ -379,6 +382,35 @@ def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chu
     cur.wait_stream(s_out)
     cur.wait_stream(s_in)
     return out
+
+
+_RATIOS = {}   # (device, subject shape, dtype, steps) -> measured copy / compute time ratio
+
+
+def _copy_compute_ratio(metric, m0_host, T, num_steps, dev):
+    """Host->device copy time of ONE subject over the time of its shoot, measured with CUDA events
+    the first time a (device, shape, dtype, steps) combination is seen; None if it cannot be
+    measured (stream capture in progress)."""
+    key = (dev.index, tuple(m0_host.shape[1:]), m0_host.dtype, int(num_steps))
+    if key in _RATIOS:
+        return _RATIOS[key]
+    if torch.cuda.is_current_stream_capturing() or m0_host.shape[0] == 0:
+        return None
+    with torch.cuda.device(dev), torch.no_grad():
+        one = m0_host[:1]
+        d = one.to(dev, non_blocking=True)
+        expmap(metric, d, T=T, num_steps=num_steps)            # warm-up: tables, allocator
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize(dev)
+        ev[0].record()
+        d.copy_(one, non_blocking=True)
+        ev[1].record()
+        expmap(metric, d, T=T, num_steps=num_steps)
+        ev[2].record()
+        torch.cuda.synchronize(dev)
+        copy_ms, shoot_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    _RATIOS[key] = copy_ms / max(shoot_ms, 1e-6)
+    return _RATIOS[key]
 
 
 _HOST_PLANS = {}   # key -> plan; at most _HOST_PLANS_MAX entries (each holds its chunks' device buffers)

@@ -89,6 +89,13 @@ def test_expmap_host_chunk_schedule(lm):
             assert c[0] == 1 and c[-1] == 1 or N <= 3, (N, steps, c)
     assert _auto_chunks(16, 10) == [1, 2, 4, 5, 3, 1]
     assert _auto_chunks(8, 5) == [1] * 8
+    # the same schedule from a measured copy / compute ratio (what expmap_host passes)
+    assert _auto_chunks(16, 10, ratio=0.48) == [1, 2, 4, 5, 3, 1]
+    assert _auto_chunks(8, 99, ratio=1.3) == [1] * 8
+    for r in (0.01, 0.1, 0.3, 0.7, 1.0, 5.0):
+        for N in (1, 2, 7, 16, 64):
+            c = _auto_chunks(N, 10, ratio=r)
+            assert sum(c) == N and min(c) >= 1 and max(c) <= 6  # cap 5, +1 when a stray single is merged
     with pytest.raises(RuntimeError, match="host tensors"):
         lm.expmap_host(lm.FluidMetric(), torch.zeros(1, 3, 4, 4, 4, device="meta") if False else _FakeCuda())
 
