@@ -24,6 +24,7 @@
 #include <vector>
 #include <cooperative_groups.h>
 #include "fft.cuh"
+#include "mixfft.cuh"
 
 namespace lgm {
 
@@ -894,6 +895,78 @@ xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
   }
 }
 
+
+// First-axis pass of the mixed-radix path: X forward -> multiplier -> X inverse in one kernel
+// (mix_xmid, mixfft.cuh). NCH = 1 for beta == 0 (scalar symbol, channels independent), NCH = D
+// otherwise (the reference's 3x3 Cholesky arithmetic on the channels of one frequency).
+template <typename R, int D, int NCH, bool INVERSE>
+__global__ void __launch_bounds__(kMixThreads)
+mix_xpass_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc, MixPlan pl, int Tsh,
+                 const typename Cx<R>::T* __restrict__ tw, const R* __restrict__ wl0, const R* __restrict__ sl0,
+                 const R* __restrict__ wl1, const R* __restrict__ sl1, const R* __restrict__ wl2,
+                 const R* __restrict__ sl2, double alpha, double beta, double gamma) {
+  using C = typename Cx<R>::T;
+  extern __shared__ __align__(16) unsigned char mixx_smem[];
+  const int T = 1 << Tsh, NX = pl.n;
+  C* bufs = reinterpret_cast<C*>(mixx_smem);                   // 2 x NCH x T x NX
+  R* ly = reinterpret_cast<R*>(bufs + (size_t)2 * NCH * T * NX);  // per line: wy, wz, sy, sz
+  const long long q0 = (long long)blockIdx.x * T;
+  const int lvalid = (int)((plane - q0 < T) ? (plane - q0) : T);
+  for (int l = threadIdx.x; l < T; l += kMixThreads) {
+    R wy = R(0), wz = R(0), sy = R(0), sz = R(0);
+    if (l < lvalid) {
+      const long long q = q0 + l;
+      if constexpr (D == 2) {
+        wy = wl1[q];
+        sy = sl1[q];
+      } else {
+        const int py = (int)(q / Zc), pz = (int)(q - (long long)py * Zc);
+        wy = wl1[py];
+        wz = wl2[pz];
+        sy = sl1[py];
+        sz = sl2[pz];
+      }
+    }
+    ly[l] = wy;
+    ly[T + l] = wz;
+    ly[2 * T + l] = sy;
+    ly[3 * T + l] = sz;
+  }
+  C* base = spec + (long long)blockIdx.y * NCH * NX * plane + q0;
+  mix_xmid<R, NCH>(base, (long long)NX * plane, plane, lvalid, pl, Tsh, tw, bufs, [&](int r, int l, C (&v)[NCH]) {
+    R w[3] = {wl0[r], ly[l], ly[T + l]};
+    if constexpr (NCH == 1) {
+      const R sw = (D == 2) ? (w[0] + w[1]) : (w[0] + w[1] + w[2]);
+      const R lambda = (R)(gamma + alpha * (double)sw);
+      const R Lm = lambda * lambda;
+      if (INVERSE) {
+        const R f = oo_sqrt_fast<R>(Lm);
+        v[0].x = (v[0].x * f) * f;
+        v[0].y = (v[0].y * f) * f;
+      } else {
+        v[0].x = Lm * v[0].x;
+        v[0].y = Lm * v[0].y;
+      }
+    } else {
+      R sn[3] = {sl0[r], ly[2 * T + l], ly[3 * T + l]};
+      Symbol<R, D> S = make_symbol<R, D, INVERSE>(w, sn, alpha, beta, gamma);
+      R re[D], im[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        re[c] = v[c].x;
+        im[c] = v[c].y;
+      }
+      apply_symbol<R, D, INVERSE>(S, re);
+      apply_symbol<R, D, INVERSE>(S, im);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        v[c].x = re[c];
+        v[c].y = im[c];
+      }
+    }
+  });
+}
+
 // ------------------------------------------------------------------------------------------
 // Direct-DFT path (any size): unitary transforms, out of place between two buffers.
 // ------------------------------------------------------------------------------------------
@@ -1264,6 +1337,151 @@ static int fluid_naive(void* out, const void* in, int64_t N, int dim, const int6
   return LGM_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Mixed-radix path (mixfft.cuh): any size whose lines fit in shared memory. Same structure as
+// the reference's rfft -> fluid_operator -> irfft (metric.py:11-19): one pass per axis each way, all
+// in place on one natural-order half spectrum, O(n log n) and coalesced.
+// ------------------------------------------------------------------------------------------
+static int mix_lines_per_cta(int n, size_t csize, bool contiguous_lines) {
+  const size_t pitch = contiguous_lines ? (size_t)(n | 1) : (size_t)n;
+  for (int T = 32; T >= 1; T /= 2)
+    if (2 * (size_t)T * pitch * csize <= 96 * 1024) return T;
+  for (int T = 1; T >= 1; --T)
+    if (2 * (size_t)T * pitch * csize <= 220 * 1024) return T;
+  return 0;
+}
+
+template <typename R>
+static bool mixed_ok(int dim, const int64_t* shape) {
+  using C = typename Cx<R>::T;
+  static const bool off = getenv("LGM_NO_MIXED_FFT") != nullptr;  // kernel experiments: direct DFT
+  if (off) return false;
+  for (int a = 0; a < dim; ++a) {
+    if (shape[a] < 2 || shape[a] > (1 << 20)) return false;
+    if (mix_lines_per_cta((int)shape[a], sizeof(C), a == dim - 1) < 1) return false;
+  }
+  long long V = 1;
+  for (int a = 0; a < dim; ++a) V *= shape[a];
+  return V / shape[dim - 1] <= 65535LL * 32;  // grid.y of the axis passes
+}
+
+template <typename R>
+static int fluid_mixed(void* out, const void* in, int64_t N, int dim, const int64_t* shape, int inverse,
+                       double alpha, double beta, double gamma, void* ws, const FluidPlan& p, cudaStream_t s) {
+  using C = typename Cx<R>::T;
+  const int nlast = (int)shape[dim - 1], nc = nlast / 2 + 1;
+  long long V = 1;
+  for (int a = 0; a < dim; ++a) V *= shape[a];
+  const long long lines = N * dim * (V / nlast);
+  C* spec = (C*)ws;
+  const R sc = (R)(1.0 / sqrt((double)V));
+  // last axis: even lengths as a half-length complex transform + split, odd ones full length
+  const bool even = (nlast % 2 == 0) && nlast >= 4 && (((uintptr_t)in | (uintptr_t)out) % sizeof(C) == 0);
+  const int nz = even ? nlast / 2 : nlast;
+  const int Tz = mix_lines_per_cta(nz, sizeof(C), true);
+  const size_t smem_z = 2 * (size_t)Tz * (nz | 1) * sizeof(C);
+  const MixPlan plz = mix_factor(nz);
+  if (even) {
+    LGM_CUDA_TRY(set_smem(mix_r2c_even_kernel<R>, smem_z), "mix_r2c smem");
+    mix_r2c_even_kernel<R><<<(unsigned)cdiv(lines, Tz), kMixThreads, smem_z, s>>>(spec, (const R*)in, lines, plz, ilog2(Tz), (const C*)p.tw[dim - 1], sc);
+  } else {
+    LGM_CUDA_TRY(set_smem(mix_r2c_kernel<R>, smem_z), "mix_r2c smem");
+    mix_r2c_kernel<R><<<(unsigned)cdiv(lines, Tz), kMixThreads, smem_z, s>>>(spec, (const R*)in, lines, plz, ilog2(Tz), (const C*)p.tw[dim - 1], sc);
+  }
+  count_launch("mix_r2c", s);
+  auto axis_pass = [&](int a, long long st, bool inv) -> int {
+    const int n = (int)shape[a];
+    const MixPlan pl = mix_factor(n);
+    const int T = mix_lines_per_cta(n, sizeof(C), false);
+    const size_t smem = 2 * (size_t)T * n * sizeof(C);
+    const long long outer = lines * nc / ((long long)n * st);
+    if (outer > 0x7fffffffLL) return set_error(LGM_EUNSUP, "lgm_fluid_apply: too many lines");
+    dim3 grid((unsigned)cdiv(st, T), 1, 1);
+    // outer count goes to grid.y in chunks of 65535
+    for (long long o0 = 0; o0 < outer; o0 += 65535) {
+      grid.y = (unsigned)((outer - o0 < 65535) ? (outer - o0) : 65535);
+      C* base = spec + o0 * n * st;
+      if (inv) {
+        LGM_CUDA_TRY(set_smem(mix_c2c_kernel<R, true>, smem), "mix_c2c smem");
+        mix_c2c_kernel<R, true><<<grid, kMixThreads, smem, s>>>(base, st, pl, ilog2(T), (const C*)p.tw[a]);
+      } else {
+        LGM_CUDA_TRY(set_smem(mix_c2c_kernel<R, false>, smem), "mix_c2c smem");
+        mix_c2c_kernel<R, false><<<grid, kMixThreads, smem, s>>>(base, st, pl, ilog2(T), (const C*)p.tw[a]);
+      }
+      count_launch("mix_c2c", s);
+    }
+    return LGM_OK;
+  };
+  long long sts[3] = {0, 0, 0};
+  {
+    long long t = nc;
+    for (int a = dim - 2; a >= 0; --a) {
+      sts[a] = t;
+      t *= shape[a];
+    }
+  }
+  // middle axes forward (3-D: Y), then the first axis with the multiplier inside, then back
+  for (int a = dim - 2; a >= 1; --a) {
+    int rc = axis_pass(a, sts[a], false);
+    if (rc) return rc;
+  }
+  {
+    const int NX = (int)shape[0];
+    const int nch = (beta == 0.0) ? 1 : dim;
+    int T = 0;
+    for (int t = 32; t >= 1; t /= 2)
+      if (2 * (size_t)nch * t * NX * sizeof(C) + 4 * t * sizeof(R) <= (t >= 8 ? 100 : 220) * 1024) { T = t; break; }
+    const long long plane = sts[0];
+    if (T >= 1 && N * dim <= 65535) {
+      const MixPlan pl = mix_factor(NX);
+      int Tsh = 0;
+      while ((1 << Tsh) < T) ++Tsh;
+      const size_t smem = 2 * (size_t)nch * T * NX * sizeof(C) + 4 * T * sizeof(R);
+      dim3 grid((unsigned)cdiv(plane, T), (unsigned)(nch == 1 ? N * dim : N));
+#define LGM_MIXX(D_, NCH_, INV_)                                                                                   \
+  do {                                                                                                             \
+    LGM_CUDA_TRY(set_smem(mix_xpass_kernel<R, D_, NCH_, INV_>, smem), "mix_xpass smem");                           \
+    mix_xpass_kernel<R, D_, NCH_, INV_><<<grid, kMixThreads, smem, s>>>(                                           \
+        spec, plane, nc, pl, Tsh, (const C*)p.tw[0], (const R*)p.wl[0], (const R*)p.sl[0], (const R*)p.wl[1],      \
+        (const R*)p.sl[1], (const R*)p.wl[2], (const R*)p.sl[2], alpha, beta, gamma);                              \
+  } while (0)
+      if (dim == 2) {
+        if (nch == 1) { if (inverse) LGM_MIXX(2, 1, true); else LGM_MIXX(2, 1, false); }
+        else { if (inverse) LGM_MIXX(2, 2, true); else LGM_MIXX(2, 2, false); }
+      } else {
+        if (nch == 1) { if (inverse) LGM_MIXX(3, 1, true); else LGM_MIXX(3, 1, false); }
+        else { if (inverse) LGM_MIXX(3, 3, true); else LGM_MIXX(3, 3, false); }
+      }
+#undef LGM_MIXX
+      count_launch("mix_xpass", s);
+    } else {  // a first axis too long for the fused tile: three separate passes
+      int rc = axis_pass(0, sts[0], false);
+      if (rc) return rc;
+      int64_t sshape[3];
+      for (int a = 0; a < dim; ++a) sshape[a] = shape[a];
+      sshape[dim - 1] = nc;
+      if (dim == 2) launch_operator<R, 2>((R*)spec, inverse, p, alpha, beta, gamma, (int)N, make_geom<2>(sshape), s);
+      else launch_operator<R, 3>((R*)spec, inverse, p, alpha, beta, gamma, (int)N, make_geom<3>(sshape), s);
+      rc = axis_pass(0, sts[0], true);
+      if (rc) return rc;
+    }
+  }
+  for (int a = 1; a <= dim - 2; ++a) {
+    int rc = axis_pass(a, sts[a], true);
+    if (rc) return rc;
+  }
+  if (even) {
+    LGM_CUDA_TRY(set_smem(mix_c2r_even_kernel<R>, smem_z), "mix_c2r smem");
+    mix_c2r_even_kernel<R><<<(unsigned)cdiv(lines, Tz), kMixThreads, smem_z, s>>>((R*)out, spec, lines, plz, ilog2(Tz), (const C*)p.tw[dim - 1], sc);
+  } else {
+    LGM_CUDA_TRY(set_smem(mix_c2r_kernel<R>, smem_z), "mix_c2r smem");
+    mix_c2r_kernel<R><<<(unsigned)cdiv(lines, Tz), kMixThreads, smem_z, s>>>((R*)out, spec, lines, plz, ilog2(Tz), (const C*)p.tw[dim - 1], sc);
+  }
+  count_launch("mix_c2r", s);
+  return LGM_OK;
+}
+
 template <typename R>
 static int64_t fluid_ws_bytes(int64_t N, int dim, const int64_t* shape) {
   long long V = 1;
@@ -1292,6 +1510,8 @@ int fluid_apply_t(void* out, const void* in, int64_t N, int dim, const int64_t* 
     if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws) & 15)
       return set_error(LGM_EINVAL, "lgm_fluid_apply: pointers must be 16-byte aligned");
     rc = fluid_fast<R>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, *p, rev, s);
+  } else if (mixed_ok<R>(dim, shape)) {
+    rc = fluid_mixed<R>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, *p, s);
   } else {
     rc = fluid_naive<R>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, *p, s);
   }

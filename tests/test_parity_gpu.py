@@ -137,6 +137,32 @@ def test_fluid_metric(lm, orc, dim, dtype, params):
         assert l2err(gm.flat(m.cuda()), om.flat(m)) <= tol, (sh, "flat")
 
 
+# sizes that are not powers of two: the mixed-radix path (csrc/mixfft.cuh): radices 4/2/3/5/7, generic
+# prime stages (13, 109, 11*11), odd last axis, mixed with power-of-two axes, typical MRI grids
+MIXED_SHAPES = {2: [(5, 7), (9, 15), (24, 40), (48, 96), (218, 26), (121, 22), (30, 1000)],
+                3: [(5, 6, 7), (12, 10, 14), (24, 40, 48), (20, 24, 20), (16, 48, 80), (26, 22, 21), (40, 48, 40)]}
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("params", FLUID_PARAMS[:2])
+def test_fluid_metric_mixed_radix(lm, orc, dim, dtype, params):
+    for sh in MIXED_SHAPES[dim]:
+        m = randn((2, dim) + sh, dtype, 63)
+        om, gm = orc.FluidMetric(params), lm.FluidMetric(params)
+        tol = 1e-5 if dtype == torch.float32 else 1e-11
+        assert l2err(gm.sharp(m.cuda()), om.sharp(m)) <= tol, (sh, "sharp")
+        assert l2err(gm.flat(m.cuda()), om.flat(m)) <= tol, (sh, "flat")
+
+
+def test_fluid_metric_mri_grid(lm, orc):
+    """one subject on a 160 x 192 x 160 grid (5*32, 3*64) and on 91 x 109 x 91 (MNI 2 mm: 7*13, prime 109)"""
+    for sh in [(160, 192, 160), (91, 109, 91)]:
+        m = randn((1, 3) + sh, torch.float32, 64)
+        om, gm = orc.FluidMetric([0.1, 0.0, 0.01]), lm.FluidMetric([0.1, 0.0, 0.01])
+        assert l2err(gm.sharp(m.cuda()), om.sharp(m)) <= 1e-5, sh
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_fluid_metric_partial_line_block(lm, orc, dtype):
     """fewer lines than one CTA of the Z pass holds (16 < 32): the padded fill path, not the edge stage"""
