@@ -81,15 +81,19 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Z % 32 == 0 (whole warps per chunk: the splat's lane exchange)
-template <int NV, bool NEED_I, bool NEED_AT>
+// XS: x slabs walked by one CTA. The d_A / d_T partial sums live in registers across all of them, so the
+// block reduction at the end (12 warp sums = 60 shuffles per warp, 12 atomics per CTA) is paid once
+// per XS * 128 voxels of a warp instead of once per 128.
+template <int NV, bool NEED_I, bool NEED_AT, int XS>
 __global__ void __launch_bounds__(256)
 affine3_bwd_kernel(float* __restrict__ d_I, float* __restrict__ d_A, float* __restrict__ d_T,
                    const float* __restrict__ go, const float* __restrict__ I, const float* __restrict__ A,
                    const float* __restrict__ T, int X, int Y, int Z, int C, size_t I_batch_stride) {
   const int j = blockIdx.y * 8 + threadIdx.y;
   const bool rowok = j < Y;  // whole warps (a warp is one row); no early return: the CTA reduces at the end
-  const int i = blockIdx.z % X;
-  const int n = blockIdx.z / X;
+  const int XB = (X + XS - 1) / XS;
+  const int i0 = (blockIdx.z % XB) * XS;
+  const int n = blockIdx.z / XB;
   const int sy = Z, sx = Y * Z;
   const int V = X * sx;
   const unsigned full = 0xffffffffu;
@@ -108,12 +112,15 @@ affine3_bwd_kernel(float* __restrict__ d_I, float* __restrict__ d_A, float* __re
     const float* In = I + (size_t)n * I_batch_stride;
     float* dIn = d_I + (size_t)n * I_batch_stride;
     const float* gn = go + (size_t)n * C * V;
-    const int row = i * sx + j * sy;
-    const float f0 = (float)i - o[0], f1 = (float)j - o[1];
+    const float f1 = (float)j - o[1];
 #pragma unroll 1
-    for (int v = 0; v < NV; ++v) {
+    for (int iv = 0; iv < XS * NV; ++iv) {
+      const int i = i0 + iv / NV, v = iv % NV;
+      if (i >= X) break;
+      const int row = i * sx + j * sy;
+      const float f0 = (float)i - o[0];
       const int kb = (blockIdx.x * NV + v) * 32;
-      if (kb >= Z) break;
+      if (kb >= Z) continue;
       const int k = kb + lane;
       const int c0 = row + k;
       const float f2 = (float)k - o[2];
@@ -230,16 +237,23 @@ int affine3_bwd_f32(void* d_I, void* d_A, void* d_T, const void* go, const void*
                     int64_t N, int64_t NI, int64_t C, const int64_t* sh, cudaStream_t s) {
   if (!affine3_ok(N, C, sh) || sh[2] % 32 != 0) return LGM_EUNSUP;
   const size_t ibs = (NI == 1 && N > 1) ? 0 : (size_t)C * sh[0] * sh[1] * sh[2];
-  dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * sh[0])), block(32, 8);
+  const dim3 block(32, 8);
   const bool need_at = d_A || d_T;
-#define LGM_AB(NI_, NAT_) \
-  affine3_bwd_kernel<4, NI_, NAT_><<<grid, block, 0, s>>>((float*)d_I, (float*)d_A, (float*)d_T, (const float*)go, \
-      (const float*)I, (const float*)A, (const float*)T, (int)sh[0], (int)sh[1], (int)sh[2], (int)C, ibs)
-  if (d_I && need_at) LGM_AB(true, true);
-  else if (d_I) LGM_AB(true, false);
-  else LGM_AB(false, true);
-#undef LGM_AB
-  count_launch("affine_bwd", s);
+  // The splat (d_I) and the pose gradients (d_A, d_T) run as TWO kernels: fused they need 104 registers
+  // (2 CTAs / SM) and take longer than the pair (measured at 16 x 192^3: 2.9 ms fused, 1.2 + 1.1 apart).
+  if (d_I) {
+    dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * sh[0]));
+    affine3_bwd_kernel<4, true, false, 1><<<grid, block, 0, s>>>((float*)d_I, nullptr, nullptr, (const float*)go,
+        (const float*)I, (const float*)A, (const float*)T, (int)sh[0], (int)sh[1], (int)sh[2], (int)C, ibs);
+    count_launch("affine_bwd_splat", s);
+  }
+  if (need_at) {
+    constexpr int XS = 8;
+    dim3 grid((unsigned)cdiv(sh[2], 128), (unsigned)cdiv(sh[1], 8), (unsigned)(N * cdiv(sh[0], XS)));
+    affine3_bwd_kernel<4, false, true, XS><<<grid, block, 0, s>>>(nullptr, (float*)d_A, (float*)d_T, (const float*)go,
+        (const float*)I, (const float*)A, (const float*)T, (int)sh[0], (int)sh[1], (int)sh[2], (int)C, ibs);
+    count_launch("affine_bwd_pose", s);
+  }
   return finish(s, "lgm_affine_interp_bwd");
 }
 
