@@ -186,6 +186,27 @@ def _blob_dataset(torch, S, n, dev, seed0=100):
     return Synth()
 
 
+def nccl_log_summary():
+    """what NCCL's own INIT log of this process says about the communicator (file set in main())"""
+    import glob
+    import re
+    pat = os.environ.get("NCCL_DEBUG_FILE", "").replace("%p", str(os.getpid()))
+    out = {"log": pat or None}
+    try:
+        txt = "".join(open(f, errors="replace").read() for f in glob.glob(pat)) if pat else ""
+        m = re.search(r"NCCL version ([0-9.+a-z]+)", txt)
+        out["version"] = m.group(1) if m else None
+        m = re.search(r"nranks (\d+)", txt)
+        out["nranks"] = int(m.group(1)) if m else None
+        out["nvls"] = bool(re.search(r"NVLS", txt)) if txt else None
+        m = re.search(r"(\d+) coll channels, (\d+) collnet channels, (\d+) nvls channels, (\d+) p2p channels", txt)
+        out["channels"] = m.group(0) if m else None
+        out["transport"] = sorted(set(re.findall(r"via (P2P/[A-Za-z/]+|SHM[A-Za-z/]*|NET/[A-Za-z]+)", txt)))[:4]
+    except Exception as e:
+        out["error"] = str(e)[:120]
+    return out
+
+
 def bench_c3_atlas(torch, dist, lm, dev, world, rank, hbm, barrier, reduce_max, K=2, W=1, n=256, per_gpu=8):
     """BASELINE config 3: one atlas epoch (lagomorph/lddmm.py:287-358) over this rank's 8 subjects of
     256^3 in one batch: 5-step expmap, deform, loss, backward through the shoot, momentum update, and
@@ -206,6 +227,7 @@ def bench_c3_atlas(torch, dist, lm, dev, world, rank, hbm, barrier, reduce_max, 
            "collective": "NCCL all_reduce of the %d MiB atlas gradient (async, overlapping the momentum update) "
                          "+ one all_reduce of 2 scalars, inside the timed region" % (n ** 3 * 4 >> 20) if world > 1
                          else "none (1 rank)",
+           "nccl": nccl_log_summary() if world > 1 else None,
            "gpu_launches_per_epoch": launches, "last_epoch_loss": b.iter_losses[-1] if b.iter_losses else None,
            "config": {"shape": [n, n, n], "subjects": S, "subjects_per_gpu": per_gpu, "batch": per_gpu,
                       "epdiff_steps": 5}}
@@ -408,8 +430,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     numa, numa_why = bind_to_gpu_numa_node(local_rank) if world > 1 else (None, "single rank: not bound")
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")          # communicator / topology lines on stderr
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # NCCL's communicator log goes to a file (stdout must stay ONE JSON line); rank 0 summarises it
+        # in also.c3_atlas.nccl
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/lgm_nccl_%d.%%p.log" % os.getppid())
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1
 
@@ -489,6 +514,26 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             res["e2e"] = {"value": world * batch * V * nsteps * K / (t.item() * 1e-3), "unit": "voxel-steps/s",
                           "h2d_bytes_per_step": m_host.numel() * 4, "d2h_bytes_per_step": h_host.numel() * 4}
+            # what the box's host<->device path allows: the same two buffers copied in both directions at
+            # once by ALL ranks together, no compute (the ceiling of any pipelined host-buffer API)
+            s2 = torch.cuda.Stream(dev)
+            d_tmp = torch.empty_like(m0)
+            barrier()
+            e0.record()
+            for _ in range(3):
+                m0.copy_(m_host, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    h_host.copy_(d_tmp, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s2)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / 3], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res["e2e"]["copy_only_ms_per_step"] = t.item()
+            res["e2e"]["copy_gbs_per_rank_both_directions"] = 2 * m_host.numel() * 4 / (t.item() * 1e-3) / 1e9
+            res["e2e"]["copy_bound_ceiling"] = world * batch * V * nsteps / (t.item() * 1e-3)
+            del d_tmp
         del m0, h
         torch.cuda.empty_cache()
         return res

@@ -382,9 +382,16 @@ int Ad_star3_f32(void* out, const void* phi, const void* m, int64_t N, const int
   return finish(s, "lgm_Ad_star_fwd");
 }
 
+int compose3_ring_f32(void* out, const void* u, const void* v, int64_t N, const int64_t* sh, double ds, double dt,
+                      int rev, cudaStream_t s);  // compose_ring.cu
+
 int compose3_f32(void* out, const void* u, const void* v, int64_t N, const int64_t* sh, double ds, double dt,
                  int rev, cudaStream_t s) {
   if (!fast3_ok(out, u, v, N, sh)) return LGM_EUNSUP;
+  {  // sub-voxel displacements on power-of-two rows: gather source staged in shared memory (TMA ring)
+    const int rc = compose3_ring_f32(out, u, v, N, sh, ds, dt, rev, s);
+    if (rc != LGM_EUNSUP) return rc;
+  }
   const float dh = (float)ds, dl = (float)(ds - (double)dh);
   constexpr int BX = LGM_GATHER_BX;
   dim3 grid((unsigned)cdiv(sh[2], 32 * LGM_GATHER_NV), (unsigned)cdiv(sh[1], (8 / BX) * LGM_GATHER_NR), (unsigned)(N * cdiv(sh[0], BX))), block(32, 8 / BX, BX);

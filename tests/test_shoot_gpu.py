@@ -84,3 +84,43 @@ def test_nonfinite_displacement_propagates(lm, axis):
         assert torch.isfinite(out).sum().item() == out.numel() - 3
         assert torch.isnan(lm.compose(u, I)[0, :, 3, 5, 7]).all()
         assert torch.isnan(lm.Ad_star(u, I)[0, :, 3, 5, 7]).all()
+
+
+_RING_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[2])
+import lagomorph_b200 as lm
+outs = {}
+for i, sh in enumerate([(8, 16, 32), (20, 24, 64), (16, 40, 128), (8, 12, 256), (5, 9, 128)]):
+    g = torch.Generator().manual_seed(10 + i)
+    u = (torch.rand((2, 3) + sh, generator=g) - 0.5) * 6.0      # |ds*u| < 0.3 voxel with ds = -0.1
+    u[0, :, :, :2, 5:9] *= 8.0                                   # a patch that leaves the staged window
+    u[1, 0, -1] += 30.0                                          # samples pushed across the x border
+    v = torch.randn((2, 3) + sh, generator=g)
+    outs["c%d" % i] = lm.compose(u.cuda(), v.cuda(), ds=-0.1, dt=1.0).cpu()
+    outs["d%d" % i] = lm.compose_disp_vel(v.cuda(), u.cuda(), dt=0.05).cpu()
+torch.save(outs, sys.argv[1])
+"""
+
+
+def test_ring_compose_bit_identical_to_planar_gather(tmp_path):
+    """compose with the gather source staged in shared memory by bulk async copies (csrc/compose_ring.cu)
+    == the planar L1 gather kernel (LGM_NO_RING=1, read once per process: hence two subprocesses),
+    bit for bit, including warps that fall back because a sample leaves the staged window."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "ring.py"
+    script.write_text(_RING_SCRIPT)
+    res = {}
+    for tag, env in (("ring", {}), ("planar", {"LGM_NO_RING": "1"})):
+        out = str(tmp_path / (tag + ".pt"))
+        e = dict(os.environ)
+        e.pop("LGM_NO_RING", None)
+        e.update(env)
+        subprocess.check_call([sys.executable, str(script), out, root], env=e)
+        res[tag] = torch.load(out)
+    assert res["ring"].keys() == res["planar"].keys() and len(res["ring"]) == 10
+    for k in res["ring"]:
+        assert torch.equal(res["ring"][k], res["planar"][k]), k
