@@ -163,8 +163,7 @@ compose_ring_kernel(float* __restrict__ out, const float* __restrict__ u, const 
           const float v3 = p01[c * CH], v7 = p01[c * CH + 1];
           const float v1 = p10[c * CH], v5 = p10[c * CH + 1];
           const float v2 = p11[c * CH], v6 = p11[c * CH + 1];
-          r[c] = omv * (omu * (omt * v0 + t * v1) + uu * (omt * v3 + t * v2)) +
-                 wv * (omu * (omt * v4 + t * v5) + uu * (omt * v7 + t * v6));
+          r[c] = lerp8(v0, v1, v2, v3, v4, v5, v6, v7, t, uu, wv, omt, omu, omv);
         }
         m0v = r[0];
         m1v = r[1];

@@ -76,6 +76,22 @@ __device__ __forceinline__ const T* at4(const T* base, unsigned idx, unsigned fo
   return (const T*)((const char*)base + (unsigned long long)idx * four);
 }
 
+// Nested lerp of the 8 corner values (corner numbering / evaluation order of include/interp.h:115-122):
+//   omv*(omu*(omt*v0 + t*v1) + u*(omt*v3 + t*v2)) + v*(omu*(omt*v4 + t*v5) + u*(omt*v7 + t*v6)).
+// Every a*x + b*y is spelled fma(b, y, a*x) explicitly, so that all kernels sampling through this
+// function (L1 gathers, the shared-memory ring of compose_ring.cu) round identically whatever
+// contraction the compiler would have picked in their context.
+__device__ __forceinline__ float lerp8(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7,
+                                       float t, float u, float v, float omt, float omu, float omv) {
+  const float a0 = __fmaf_rn(t, v1, __fmul_rn(omt, v0));
+  const float a1 = __fmaf_rn(t, v2, __fmul_rn(omt, v3));
+  const float a2 = __fmaf_rn(t, v5, __fmul_rn(omt, v4));
+  const float a3 = __fmaf_rn(t, v6, __fmul_rn(omt, v7));
+  const float b0 = __fmaf_rn(u, a1, __fmul_rn(omu, a0));
+  const float b1 = __fmaf_rn(u, a3, __fmul_rn(omu, a2));
+  return __fmaf_rn(v, b1, __fmul_rn(omv, b0));
+}
+
 // 8-corner gather + nested lerp (corner numbering / evaluation order of include/interp.h:91-122).
 // i00..i11 are the element indices of the four (x,y) corner rows at the lower z corner; the upper z
 // corner is always the +1 neighbour (an immediate offset on the same address register), see z_pair().
@@ -90,8 +106,7 @@ __device__ __forceinline__ float trilerp(const float* __restrict__ img, unsigned
   float v3 = __ldg(p01), v7 = __ldg(p01 + 1);
   float v1 = __ldg(p10), v5 = __ldg(p10 + 1);
   float v2 = __ldg(p11), v6 = __ldg(p11 + 1);
-  return omv * (omu * (omt * v0 + t * v1) + u * (omt * v3 + t * v2)) +
-         v * (omu * (omt * v4 + t * v5) + u * (omt * v7 + t * v6));
+  return lerp8(v0, v1, v2, v3, v4, v5, v6, v7, t, u, v, omt, omu, omv);
 }
 
 // Along the contiguous axis the two corners are fetched as (zs, zs+1) with zs <= Z-2 so that the
