@@ -568,7 +568,7 @@ def main():
         breakdown[k] = entry
     if dom is not None and "achieved_gbs" in breakdown[dom]:
         traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
-        tname = {"c2": "r1_traffic.json", "c3": "r1_traffic_c3.json"}.get(args.workload)
+        tname = {"c2": "r2_traffic.json", "c3": "r2_traffic_c3.json"}.get(args.workload)
         tpath = os.path.join(ROOT, "profiles", tname) if tname else None
         if tpath and os.path.exists(tpath):
             t = json.load(open(tpath)).get(dom)

@@ -19,8 +19,11 @@
 #ifndef LGM_RING_XS
 #define LGM_RING_XS 16  /* x slabs marched by one CTA */
 #endif
+#ifndef LGM_RING_PF
+#define LGM_RING_PF 2  /* L2 prefetch of the velocity rows this many slabs ahead (0 = off); 2 measured best of 2/4/8 */
+#endif
 #ifndef LGM_RING_MINB
-#define LGM_RING_MINB 3
+#define LGM_RING_MINB 2  /* 2 measured best (C2 0.269 ms vs 0.283 at 3, 0.282 at 4): registers for loads in flight */
 #endif
 
 namespace lgm {
@@ -115,6 +118,11 @@ compose_ring_kernel(float* __restrict__ out, const float* __restrict__ u, const 
   for (int x = xs0; x < xs1; ++x) {
     __syncthreads();  // slab x-1 is done everywhere: the slot of plane x-2 may be overwritten by plane x+2
     if (tid == 0) issue(x + 2);  // look-ahead (planes up to xs0+1 were issued in the prologue)
+    if (LGM_RING_PF > 0 && tid >= 32 && tid < 35 && x + LGM_RING_PF < xs1 && y0t + TY <= Y) {
+      // the centre loads of slab x + LGM_RING_PF (velocity rows of this tile) -> L2
+      const float* src = un + (size_t)(tid - 32) * V + (size_t)(x + LGM_RING_PF) * sx + (size_t)y0t * Z;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((unsigned)(TY * Z * 4)) : "memory");
+    }
     const int need = min(x + 1, phi_);
     while (waited < need) {
       ++waited;

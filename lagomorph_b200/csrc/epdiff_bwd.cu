@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(256)
 compose_bwd3_kernel(float* __restrict__ dv, float* __restrict__ S, const float* __restrict__ G,
                     const float* __restrict__ phi, const float* __restrict__ vel, int X, int Y, int Z,
                     float dh, float dl, float dsf) {
+  LGM_PREFETCH_ROWS_AHEAD(9, (threadIdx.x < 3 ? vel : (threadIdx.x < 6 ? G : phi)), X, Y, Z, 0)
   const int j = blockIdx.y * 8 + threadIdx.y;
   if (j >= Y) return;  // warp-uniform
   const int i = blockIdx.z % X;
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(256)
 adstar_bwd3_kernel(float* __restrict__ mi_out, float* __restrict__ d_m0, float* __restrict__ S,
                    const float* __restrict__ phi, const float* __restrict__ dm, const float* __restrict__ m0,
                    int X, int Y, int Z) {
+  LGM_PREFETCH_ROWS_AHEAD(9, (threadIdx.x < 3 ? phi : (threadIdx.x < 6 ? dm : m0)), X, Y, Z, 0)
   const int j = blockIdx.y * 8 + threadIdx.y;
   if (j >= Y) return;
   const int i = blockIdx.z % X;
@@ -246,6 +248,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 stencil_bwd3_kernel(float* __restrict__ G, float* __restrict__ S, const float* __restrict__ mi,
                     const float* __restrict__ dm, int X, int Y, int Z) {
+  LGM_PREFETCH_ROWS_AHEAD(9, (threadIdx.x < 3 ? mi : (threadIdx.x < 6 ? dm : S)), X, Y, Z, 0)
   const int j = blockIdx.y * 8 + threadIdx.y;
   if (j >= Y) return;
   const int i = blockIdx.z % X;

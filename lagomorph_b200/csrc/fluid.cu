@@ -261,6 +261,31 @@ static int get_plan(int dim, const int64_t* shape, cudaStream_t s, const FluidPl
 // ------------------------------------------------------------------------------------------
 // Fast path kernels
 // ------------------------------------------------------------------------------------------
+// L2 prefetch of the input of a LATER CTA (bulk prefetch, no shared memory, one instruction issued
+// by one thread): the slab kernels start with a burst of global loads whose DRAM latency only the
+// other CTAs of the SM hide; pulling the slab that the CTA a few hundred positions ahead
+// will read into L2 now turns those loads into L2 hits. Distances (in CTAs, 0 = off) per kernel:
+// measured on B200 (profiles/r2_notes.md): slab_fwd / slab_inv 0.190 -> 0.172 ms at C2 with 74..148,
+// cslab_fwd 1.09 -> 1.02 and cslab_inv 1.21 -> 1.06 ms at C3 with 148..296; the X pass gets slower (off).
+#ifndef LGM_PF_SLAB_FWD
+#define LGM_PF_SLAB_FWD 111
+#endif
+#ifndef LGM_PF_SLAB_INV
+#define LGM_PF_SLAB_INV 111
+#endif
+#ifndef LGM_PF_CSLAB_FWD
+#define LGM_PF_CSLAB_FWD 222
+#endif
+#ifndef LGM_PF_CSLAB_INV
+#define LGM_PF_CSLAB_INV 222
+#endif
+#ifndef LGM_PF_XPASS
+#define LGM_PF_XPASS 0
+#endif
+__device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 #ifndef LGM_SLAB_IO_UNROLL
 #define LGM_SLAB_IO_UNROLL 8  /* loads in flight per thread in slab_fwd's fill loop: 4 -> 8 = 0.244 -> 0.224 ms */
 #endif
@@ -384,6 +409,10 @@ slab_fwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in,
   C* twM = twz + Z;                          // M entries (W_M^j = W_Z^2j)
   C* twy = twM + M;                          // Y entries
   const int tid = threadIdx.x;
+  if (LGM_PF_SLAB_FWD > 0 && tid == 0 && blockIdx.x + LGM_PF_SLAB_FWD < gridDim.x) {
+    const long long nb = rev ? (long long)bx - LGM_PF_SLAB_FWD : (long long)bx + LGM_PF_SLAB_FWD;
+    l2_prefetch(in + (size_t)nb * Y * Z, (unsigned)(Y * Z * sizeof(R)));
+  }
   for (int j = tid; j < Z; j += kFftThreads) twz[j] = twz_g[j];
   for (int j = tid; j < M; j += kFftThreads) twM[j] = twz_g[2 * j];
   for (int j = tid; j < Y; j += kFftThreads) twy[j] = twy_g[j];
@@ -421,6 +450,10 @@ slab_inv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec,
   C* twM = twz + Z;
   C* twy = twM + M;
   const int tid = threadIdx.x;
+  if (LGM_PF_SLAB_INV > 0 && tid == 0 && blockIdx.x + LGM_PF_SLAB_INV < gridDim.x) {
+    const long long nb = rev ? (long long)bx - LGM_PF_SLAB_INV : (long long)bx + LGM_PF_SLAB_INV;
+    l2_prefetch(spec + (size_t)nb * Y * ZC, (unsigned)(Y * ZC * sizeof(C)));
+  }
   for (int j = tid; j < Z; j += kFftThreads) twz[j] = twz_g[j];
   for (int j = tid; j < M; j += kFftThreads) twM[j] = twz_g[2 * j];
   for (int j = tid; j < Y; j += kFftThreads) twy[j] = twy_g[j];
@@ -525,6 +558,11 @@ cslab_fwd_kernel(float2* __restrict__ spec, const float* __restrict__ in, const 
   for (int j = tid; j < M; j += kCsThreads) twM[j] = twz_g[2 * j];
   for (int j = tid; j < Y; j += kCsThreads) twy[j] = twy_g[j];
   float2* in2 = reinterpret_cast<float2*>(const_cast<float*>(in)) + (slab * Y + rank * kCsYL) * M;
+  if (LGM_PF_CSLAB_FWD > 0 && tid == 0 && blockIdx.x + LGM_PF_CSLAB_FWD < gridDim.x) {
+    const long long d = LGM_PF_CSLAB_FWD / kCsNC;
+    const long long ns = rev ? (long long)slab - d : (long long)slab + d;
+    l2_prefetch(in + ((size_t)ns * Y + rank * kCsYL) * Z, (unsigned)(kCsYL * Z * sizeof(float)));
+  }
   __syncthreads();
   // Z: half-length complex FFT (16 x 8) on panel rows; first stage straight from global memory, the
   // real split fused into the last one
@@ -557,6 +595,11 @@ cslab_inv_kernel(float* __restrict__ out, const float2* __restrict__ spec, const
   for (int j = tid; j < M; j += kCsThreads) twM[j] = twz_g[2 * j];
   for (int j = tid; j < Y; j += kCsThreads) twy[j] = twy_g[j];
   __syncthreads();
+  if (LGM_PF_CSLAB_INV > 0 && tid == 0 && rank == 0 && blockIdx.x + LGM_PF_CSLAB_INV < gridDim.x) {
+    const long long d = LGM_PF_CSLAB_INV / kCsNC;
+    const long long ns = rev ? (long long)slab - d : (long long)slab + d;
+    l2_prefetch(spec + (size_t)ns * Y * ZC, (unsigned)(Y * ZC * sizeof(float2)));
+  }
   GSide<float2> gin{const_cast<float2*>(spec) + slab * Y * ZC + rank * 32, ZC, rank == 0 ? 33 : 32, 32, M - 32};
   if (rank == 0) cslab_ypass<true, 33>(tile, twy, tid, gin);
   else cslab_ypass<true, 32>(tile, twy, tid, gin);
@@ -751,6 +794,17 @@ xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
   const long long q0 = (long long)bx * T;
   const int lvalid = (int)((plane - q0 < T) ? (plane - q0) : T);
   C* base = spec + (long long)by * NCH * NX * plane + q0;
+  if (LGM_PF_XPASS > 0 && sizeof(R) == 4) {  // rows of the tile LGM_PF_XPASS blocks ahead in launch order
+    const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + LGM_PF_XPASS;
+    if (lin < (long long)gridDim.x * gridDim.y) {
+      const unsigned pbx0 = (unsigned)(lin % gridDim.x), pby0 = (unsigned)(lin / gridDim.x);
+      const unsigned pbx = rev ? gridDim.x - 1 - pbx0 : pbx0, pby = rev ? gridDim.y - 1 - pby0 : pby0;
+      const long long pq0 = (long long)pbx * T;
+      if (plane - pq0 >= T)
+        for (int r = tid; r < NCH * NX; r += kFftThreads)
+          l2_prefetch(spec + (long long)pby * NCH * NX * plane + (long long)r * plane + pq0, (unsigned)(T * sizeof(C)));
+    }
+  }
   // per-thread (y,z) part of the symbol
   const int l = tid % T;
   R wy = R(0), wz = R(0), sy = R(0), sz = R(0);

@@ -58,6 +58,7 @@ gather3_kernel(float* __restrict__ out, const float* __restrict__ a, const float
   // rev: walk the grid from its far end (the EPDiff drivers alternate it from kernel to kernel)
   const unsigned bz = rev ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
   const unsigned by = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  if (BX == 1 && NR == 1) LGM_PREFETCH_ROWS_AHEAD(6, (threadIdx.x < 3 ? a : b), X, Y, Z, rev)
   // a thread owns NR rows (j, j + 8/BX, ...) x NV chunks: NR * NV voxels, all centre loads up front
   const int j = by * (8 / BX) * NR + threadIdx.y;
   const int XB = (X + BX - 1) / BX;
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(256)
 interp3_kernel(float* __restrict__ out, const float* __restrict__ I, const float* __restrict__ u, int X,
                int Y, int Z, int C_rt, size_t I_batch_stride, float dh, float dl) {
   const int C = CC ? CC : C_rt;
+  LGM_PREFETCH_ROWS_AHEAD(3, u, X, Y, Z, 0)
   const int j = blockIdx.y * 8 + threadIdx.y;
   if (j >= Y) return;
   const int i = blockIdx.z % X;

@@ -119,6 +119,33 @@ __device__ __forceinline__ void z_pair(const Ax3& az, int Z, int& zs, float& v) 
   if (az.i1 == az.i0) v = __fmaf_rn(az.t, 0.f, (az.i0 == 0) ? 0.f : 1.f);  // keeps a NaN weight NaN
 }
 
+// L2 prefetch for the row-walking kernels (grid = (z chunks, y tiles of 8 rows, N * X), blockDim = (32, 8)):
+// thread t < NTHR of warp 0 of the CTAs with blockIdx.x == 0 pulls the 8 rows x Z of channel (t % 3) of
+// volume SEL (an expression of t choosing among the kernel's 3-channel inputs) that the CTA LGM_PF_ROWS
+// (y, z) grid positions AHEAD in launch order will read first. These kernels open with loads whose DRAM
+// latency only the other resident CTAs hide; with the rows already in L2 that latency is an L2 hit
+// (measured on B200: Ad_star 0.444 -> 0.399 ms at C2, 1.745 -> 1.485 ms at C3; an empty asm in place of
+// the prefetch instruction gives 0.444, so it is the prefetch, not a scheduling side effect).
+// A macro, not a function: the function form of the same code measured no gain (profiles/r2_notes.md).
+#ifndef LGM_PF_ROWS
+#define LGM_PF_ROWS 148  /* distance in CTAs; 0 = off */
+#endif
+#define LGM_PREFETCH_ROWS_AHEAD(NTHR, SEL, X, Y, Z, REV)                                                          \
+  if (LGM_PF_ROWS > 0 && blockIdx.x == 0 && threadIdx.y == 0 && threadIdx.x < (NTHR)) {                            \
+    const unsigned long long lin_ = (unsigned long long)blockIdx.z * gridDim.y + blockIdx.y + LGM_PF_ROWS;         \
+    if (lin_ < (unsigned long long)gridDim.y * gridDim.z) {                                                        \
+      const unsigned pby0_ = (unsigned)(lin_ % gridDim.y), pbz0_ = (unsigned)(lin_ / gridDim.y);                   \
+      const unsigned pby_ = (REV) ? gridDim.y - 1 - pby0_ : pby0_, pbz_ = (REV) ? gridDim.z - 1 - pbz0_ : pbz0_;   \
+      const int pj_ = pby_ * 8, pi_ = pbz_ % (X), pn_ = pbz_ / (X);                                                \
+      if (pj_ + 8 <= (Y) && ((Z) & 3) == 0) {                                                                      \
+        const float* src_ = (SEL) + ((size_t)pn_ * 3 + threadIdx.x % 3) * ((size_t)(X) * (Y) * (Z)) +              \
+                            ((size_t)pi_ * (Y) + pj_) * (Z);                                                       \
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_), "r"((unsigned)(8 * (Z) * 4))        \
+                     : "memory");                                                                                  \
+      }                                                                                                            \
+    }                                                                                                              \
+  }
+
 // RN_f32(g * d) for a double d = dh + dl: stands in for the reference's "(float)((double)g * dt)"
 // (cuda/interp.cu:230) without fp64 instructions; equal except for rare double-rounding ties (1 ulp).
 __device__ __forceinline__ float mul_f32_by_double(float g, float dh, float dl) {
