@@ -22,6 +22,13 @@ m0 = torch.randn((2, 3) + sh, device=dev)
 m0 = m0 * (3.0 / met.sharp(m0).abs().max())
 h = lm.expmap(met, m0, num_steps=3)
 print("shoot", float(h.abs().max()))
+# compose through the shared-memory ring (bulk async copies + mbarriers) for every supported row length,
+# incl. warps that fall back to the global gather and tiles at the volume border
+for shp in [(6, 10, 32), (9, 12, 64), (7, 20, 128), (5, 9, 256)]:
+    u = (torch.rand((2, 3) + shp, device=dev) - 0.5) * 6.0
+    u[0, :, :, :2, 3:7] *= 8.0
+    v = torch.randn((2, 3) + shp, device=dev)
+    print("ring", shp, float(lm.compose(u, v, ds=-0.1, dt=1.0).abs().max()))
 m0g = m0.clone().requires_grad_(True)
 I = torch.randn((1, 1) + sh, device=dev, requires_grad=True)
 hh = lm.expmap(met, m0g, num_steps=2)
