@@ -58,11 +58,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 
 // WPR warps share one z row (Z = 128 * WPR for Z > 128), a CTA of 8 warps covers TY = 8 / WPR rows;
 // NV chunks of 32 per thread. blockDim = (32, 8).
+// Z is a compile-time constant (32 * NV * WPR): every offset inside the ring is an immediate.
 template <int NV, int WPR>
 __global__ void __launch_bounds__(256, LGM_RING_MINB)
 compose_ring_kernel(float* __restrict__ out, const float* __restrict__ u, const float* __restrict__ v, int X, int Y,
-                    int Z, float dh, float dl, float dsr, float dtr, int rev) {
-  constexpr int TY = 8 / WPR, ROWS = TY + 2;
+                    float dh, float dl, float dsr, float dtr, int rev) {
+  constexpr int TY = 8 / WPR, ROWS = TY + 2, Z = 32 * NV * WPR;
   extern __shared__ __align__(128) unsigned char ring_raw[];
   float* ring = reinterpret_cast<float*>(ring_raw);                 // [kRing][3][ROWS][Z]
   unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)kRing * 3 * ROWS * Z);
@@ -78,7 +79,7 @@ compose_ring_kernel(float* __restrict__ out, const float* __restrict__ u, const 
   const int V = X * sx;
   const int ylo = max(yb, 0), yhi = min(y0t + TY, Y - 1);             // staged rows of every plane
   const unsigned plane_bytes = (unsigned)((yhi - ylo + 1) * Z * 4);
-  const int CH = ROWS * Z;                                             // channel stride inside a ring slot
+  constexpr int CH = ROWS * Z;                                         // channel stride inside a ring slot
   const float* un = u + (size_t)n * 3 * V;
   const float* vn = v + (size_t)n * 3 * V;
   const float* vn1 = vn + V;
@@ -212,7 +213,7 @@ int compose3_ring_f32(void* out, const void* u, const void* v, int64_t N, const 
                                          (int)smem);                                                                 \
     if (e != cudaSuccess) return set_error((int)e, "compose ring smem: %s", cudaGetErrorString(e));                  \
     compose_ring_kernel<NV_, WPR_><<<grid, block, smem, s>>>((float*)out, (const float*)u, (const float*)v, (int)X,   \
-                                                             (int)Y, (int)Z, dh, dl, (float)ds, (float)dt, rev);     \
+                                                             (int)Y, dh, dl, (float)ds, (float)dt, rev);             \
   } while (0)
   if (Z == 32) LGM_RING(1, 1);
   else if (Z == 64) LGM_RING(2, 1);
