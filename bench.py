@@ -345,22 +345,32 @@ def bench_ref_cuda(torch, metric, lm, dev, n=128, batch=2, steps=10):
             "product_vs_reference_max_rel_err": err}
 
 
-def cpu_port_throughput(shape, batch, steps, reps=1):
-    """voxel-steps/s of the CPU oracle (OpenMP kernels + torch.fft/MKL) on a bounded sample."""
+def cpu_port_throughput(shape, steps, reps=2, warmup=1, batch=1):
+    """voxel-steps/s of the CPU oracle (OpenMP kernels + torch.fft/MKL) on a bounded sample: `batch`
+    subjects, `warmup` one-step shoots (FFT plans, page faults), then `reps` full shoots timed together.
+    ONE procedure for the cpu_baseline leg of the main arm and for `--impl reference`, so that the two
+    report the same number on the same box. Returns (value, seconds, cores, sample text)."""
+    # torchrun exports OMP_NUM_THREADS=1; the baseline is supposed to use every host core
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)
+    os.environ["MKL_NUM_THREADS"] = str(ncpu)
     import torch
+    torch.set_num_threads(ncpu)
     from oracle import oracle as orc
     orc.lib()
     met = orc.FluidMetric(PARAMS)
     m0 = make_momenta(batch, shape, 1)
     m0 = m0 * (4.0 / met.sharp(m0).abs().max())
-    best = None
+    for _ in range(warmup):
+        orc.expmap(met, m0, num_steps=1)
+    t0 = time.perf_counter()
     for _ in range(reps):
-        t0 = time.perf_counter()
         orc.expmap(met, m0, num_steps=steps)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
+    dt = time.perf_counter() - t0
     V = shape[0] * shape[1] * shape[2]
-    return batch * V * steps / best, best
+    sample = "%d subject(s) of %dx%dx%d, %d EPDiff steps, %d shoot(s) after %d warm-up step(s) (%.1f s)" % (
+        (batch,) + tuple(shape) + (steps, reps, warmup, dt))
+    return batch * V * steps * reps / dt, dt, torch.get_num_threads(), sample
 
 
 def run_reference(args):
@@ -368,29 +378,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # torchrun exports OMP_NUM_THREADS=1; this arm is supposed to use every host core
-    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    os.environ["OMP_NUM_THREADS"] = str(ncpu)
-    os.environ["MKL_NUM_THREADS"] = str(ncpu)
-    import torch
-    torch.set_num_threads(ncpu)
     batch, shape, nsteps = WORKLOADS[args.workload]
-    sample_batch = 1
-    V = shape[0] * shape[1] * shape[2]
-    from oracle import oracle as orc
-    orc.lib()
-    met = orc.FluidMetric(PARAMS)
-    m0 = make_momenta(sample_batch, shape, 1)
-    m0 = m0 * (4.0 / met.sharp(m0).abs().max())
-    for _ in range(args.warmup):
-        orc.expmap(met, m0, num_steps=1)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.expmap(met, m0, num_steps=nsteps)
-    dt = time.perf_counter() - t0
-    val = sample_batch * V * nsteps * args.steps / dt
-    cores = torch.get_num_threads()
-    sample = "%d subject(s) of %dx%dx%d, %d EPDiff steps per bench step" % ((sample_batch,) + tuple(shape) + (nsteps,))
+    val, dt, cores, sample = cpu_port_throughput(shape, nsteps, reps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": "3D voxel-steps/sec (EPDiff shoot)", "value": val, "unit": "voxel-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -613,10 +602,8 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        torch.set_num_threads(len(os.sched_getaffinity(0)))
-        val, secs = cpu_port_throughput(shape, 2, nsteps)
-        cpu = {"value": val, "unit": "voxel-steps/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "2 subjects of %dx%dx%d, %d EPDiff steps (%.1f s)" % (tuple(shape) + (nsteps, secs))}
+        val, secs, cores, sample = cpu_port_throughput(shape, nsteps, reps=3, warmup=3)
+        cpu = {"value": val, "unit": "voxel-steps/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
         line = {
