@@ -123,9 +123,29 @@ __device__ __forceinline__ C mul_w16(C t, int j) {
   return r;
 }
 
+// multiply by e^{-+ 2 pi i j/32}, j in 0..15 compile-time after unrolling (even j: the mul_w16 cases,
+// so radices <= 16 are unchanged); used by the 32-point register DFT of the quarter-slab X pass
+template <bool INV, typename C>
+__device__ __forceinline__ C mul_w32(C t, int j) {
+  using R = decltype(t.x);
+  if ((j & 1) == 0) return mul_w16<INV>(t, j >> 1);
+  constexpr double cs[8] = {0.98078528040323044913, 0.83146961230254523708, 0.55557023301960222474,
+                            0.19509032201612826785, -0.19509032201612826785, -0.55557023301960222474,
+                            -0.83146961230254523708, -0.98078528040323044913};   // cos(2 pi j/32), j = 1,3,..,15
+  constexpr double sn[8] = {0.19509032201612826785, 0.55557023301960222474, 0.83146961230254523708,
+                            0.98078528040323044913, 0.98078528040323044913, 0.83146961230254523708,
+                            0.55557023301960222474, 0.19509032201612826785};    // sin(2 pi j/32)
+  const R wr = R(cs[(j >> 1) & 7]), wi = R(sn[(j >> 1) & 7]);
+  C r;
+  if (!INV) { r.x = t.x * wr + t.y * wi; r.y = t.y * wr - t.x * wi; }
+  else { r.x = t.x * wr - t.y * wi; r.y = t.y * wr + t.x * wi; }
+  return r;
+}
+
 // RAD-point DFT in registers (radix-2 DIF). On return x[i] holds output bitrev(i).
 template <int RAD, bool INV, typename C>
 __device__ __forceinline__ void reg_fft(C (&x)[RAD]) {
+  static_assert(RAD <= 32, "register DFT of at most 32 points");
 #pragma unroll
   for (int half = RAD / 2; half >= 1; half >>= 1) {
 #pragma unroll
@@ -134,7 +154,8 @@ __device__ __forceinline__ void reg_fft(C (&x)[RAD]) {
       for (int i = 0; i < half; ++i) {
         C a = x[base + i], b = x[base + i + half];
         x[base + i] = cadd(a, b);
-        x[base + i + half] = mul_w16<INV>(csub(a, b), i * (8 / half));
+        if constexpr (RAD == 32) x[base + i + half] = mul_w32<INV>(csub(a, b), i * (16 / half));
+        else x[base + i + half] = mul_w16<INV>(csub(a, b), i * (8 / half));
       }
     }
   }
@@ -648,7 +669,7 @@ __device__ __forceinline__ void real_edge_stage(typename Cx<R>::T* tile, int rs,
 template <typename R, int M, int RAD, int L, bool INV, int JSH = 0>
 __device__ __forceinline__ void zedge_stage(typename Cx<R>::T* __restrict__ g, typename Cx<R>::T* tile, int rs,
                                             const typename Cx<R>::T* __restrict__ tw, int tid, int nth,
-                                            int jump = 0) {
+                                            int jump = 0, int lstride = M) {  // lstride: words between lines
   using C = typename Cx<R>::T;
   constexpr int SUB = M / RAD;
   constexpr int W = SUB < 32 ? 32 / SUB : 1;   // lines per warp
@@ -662,7 +683,7 @@ __device__ __forceinline__ void zedge_stage(typename Cx<R>::T* __restrict__ g, t
   for (int it = tid; it < L * SUB; it += nth) {
     const int rest = it % SUB, slot = it / SUB;
     const int l = (SUB < 32) ? (slot / 32) * 32 + (slot % W) * SUB + (slot % 32) / W : slot;
-    C* gp = g + (size_t)l * M + rest;
+    C* gp = g + (size_t)l * lstride + rest;
     C* p = tile + rest * rs + l;
     auto jo = [&](int n) -> int { return JSH > 0 ? ((rest + n * SUB) >> JSH) * jump : 0; };
     C x[RAD];
@@ -697,11 +718,11 @@ __device__ __forceinline__ void zedge_stage(typename Cx<R>::T* __restrict__ g, t
 template <typename R, int M, int L>
 __device__ __forceinline__ void real_fft_fwd_g(const R* g, typename Cx<R>::T* tile, int rs,
                                                const typename Cx<R>::T* twM, const typename Cx<R>::T* twz,
-                                               int tid, int nth) {
+                                               int tid, int nth, int lstride = M) {
   using C = typename Cx<R>::T;
   constexpr int RAD0 = 1 << stage_bits(ilog2(M), 0);
   static_assert((ilog2(M) + 3) / 4 >= 2, "real_fft_fwd_g needs two radix stages");
-  zedge_stage<R, M, RAD0, L, false>(reinterpret_cast<C*>(const_cast<R*>(g)), tile, rs, twM, tid, nth);
+  zedge_stage<R, M, RAD0, L, false>(reinterpret_cast<C*>(const_cast<R*>(g)), tile, rs, twM, tid, nth, 0, lstride);
   __syncthreads();
   if constexpr (!ColFFT<R, M, M / RAD0, 1, L>::LASTSTAGE) {
     ColFFT<R, M, M / RAD0, 1, L>::fwd_nolast(tile, rs, 1, twM, tid, nth);
@@ -712,7 +733,7 @@ __device__ __forceinline__ void real_fft_fwd_g(const R* g, typename Cx<R>::T* ti
 template <typename R, int M, int L>
 __device__ __forceinline__ void real_fft_inv_g(R* g, typename Cx<R>::T* tile, int rs,
                                                const typename Cx<R>::T* twM, const typename Cx<R>::T* twz,
-                                               int tid, int nth) {
+                                               int tid, int nth, int lstride = M) {
   using C = typename Cx<R>::T;
   constexpr int RAD0 = 1 << stage_bits(ilog2(M), 0);
   real_edge_stage<R, M, L, true>(tile, rs, 1, twz, tid, nth);
@@ -721,7 +742,7 @@ __device__ __forceinline__ void real_fft_inv_g(R* g, typename Cx<R>::T* tile, in
     ColFFT<R, M, M / RAD0, 1, L>::inv_nolast(tile, rs, 1, twM, tid, nth);
     __syncthreads();
   }
-  zedge_stage<R, M, RAD0, L, true>(reinterpret_cast<C*>(g), tile, rs, twM, tid, nth);
+  zedge_stage<R, M, RAD0, L, true>(reinterpret_cast<C*>(g), tile, rs, twM, tid, nth, 0, lstride);
 }
 
 // real forward: tile rows 0..M-1 hold z[j] = (x[2j], x[2j+1]); on return rows 0..M hold the half

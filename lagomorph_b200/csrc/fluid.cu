@@ -177,7 +177,18 @@ struct FluidPlan {
   void* wl[3] = {nullptr, nullptr, nullptr};  // 2(1-cos) LUT, storage order
   void* sl[3] = {nullptr, nullptr, nullptr};  // sin LUT, storage order
   void* tw[3] = {nullptr, nullptr, nullptr};  // e^{-2 pi i j/n}, n entries (complex)
+  // quarter-slab path (qslab.cuh): X LUT in the (X/8) x 8 storage order, Y LUT as [r][kpos]
+  bool qslab = false;
+  void* q_lx = nullptr;
+  void* q_wy = nullptr;
 };
+
+// shapes served by the quarter-slab kernels (fp32, beta == 0 decided per call)
+template <typename R>
+static bool qslab_shape(int dim, const int64_t* shape) {
+  return sizeof(R) == 4 && dim == 3 && shape[1] == 256 && shape[2] == 256 &&
+         (shape[0] == 64 || shape[0] == 128 || shape[0] == 256);
+}
 
 static bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
 
@@ -252,6 +263,24 @@ static int get_plan(int dim, const int64_t* shape, cudaStream_t s, const FluidPl
     cudaMemcpy(p.wl[a], wl.data(), sizeof(R) * wl.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(p.sl[a], sl.data(), sizeof(R) * sl.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(p.tw[a], tw.data(), sizeof(C) * tw.size(), cudaMemcpyHostToDevice);
+  }
+  if (p.fast && qslab_shape<R>(dim, shape)) {
+    const int NX = (int)shape[0], NY = (int)shape[1], YQ = NY / 4, R0 = NX / 8;
+    std::vector<float> lx(NX), wy(4 * YQ);
+    for (int rho = 0; rho < NX; ++rho) {
+      const int kx = rho / 8 + R0 * (rho % 8);
+      lx[rho] = (float)(2.0 * (1.0 - cos(2.0 * M_PI * (double)kx / (double)NX)));
+    }
+    for (int kk = 0; kk < YQ; ++kk)
+      for (int r = 0; r < 4; ++r)
+        wy[r * YQ + fft_pos_rt(YQ, kk)] = (float)(2.0 * (1.0 - cos(2.0 * M_PI * (double)(kk + YQ * r) / (double)NY)));
+    cudaError_t e;
+    if ((e = cudaMalloc(&p.q_lx, sizeof(float) * lx.size())) != cudaSuccess ||
+        (e = cudaMalloc(&p.q_wy, sizeof(float) * wy.size())) != cudaSuccess)
+      return set_error((int)e, "lgm_fluid_apply: table allocation failed: %s", cudaGetErrorString(e));
+    cudaMemcpy(p.q_lx, lx.data(), sizeof(float) * lx.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.q_wy, wy.data(), sizeof(float) * wy.size(), cudaMemcpyHostToDevice);
+    p.qslab = true;
   }
   auto ins = g_plans.emplace(key, p);
   *out = &ins.first->second;
@@ -770,6 +799,24 @@ __device__ __forceinline__ R oo_sqrt_fast(R x) {
   }
 }
 
+// 1 / safe_sqrt(lambda^2) of the beta == 0 symbol without the square root: in binary round-to-nearest
+// arithmetic sqrt(fl(x*x)) == |x| exactly (no over-/underflow: Lm <= 1e-8f is the safe_sqrt branch --
+// for a float x, (double)x < 1e-8 <=> x <= 1e-8f -- and an infinite Lm keeps sqrt's infinity), so the
+// result is bit-identical to oo_sqrt_fast(Lm) at a third of its instructions (no MUFU.RSQ + fix-up).
+template <typename R>
+__device__ __forceinline__ R oo_lambda_fast(R lambda, R Lm) {
+  if constexpr (sizeof(R) == 4) {
+    const float s = (Lm <= 1e-8f) ? 1e-4f : (Lm == INFINITY ? Lm : fabsf(lambda));
+    return (R)__frcp_rn(s);
+  } else {
+    return oo_sqrt<R>(Lm);
+  }
+}
+
+}  // namespace lgm
+#include "qslab.cuh"
+namespace lgm {
+
 template <typename R, int NX, int T, int D, int NCH, bool INVERSE>
 __global__ void __launch_bounds__(kFftThreads, (sizeof(R) == 4 && NCH == 1) ? (NX <= 128 ? LGM_XPASS_MINBLOCKS : 3) : 2)
 xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
@@ -839,7 +886,7 @@ xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
       const R lambda = (R)(gamma + alpha * (double)sw);
       const R Lm = lambda * lambda;
       if (INVERSE) {
-        const R f = oo_sqrt_fast<R>(Lm);
+        const R f = oo_lambda_fast<R>(lambda, Lm);
         v.x = ((v.x * f) * f) * scale;
         v.y = ((v.y * f) * f) * scale;
       } else {
@@ -912,7 +959,7 @@ xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
       const R Lm = lambda * lambda;
       C v = tile[idx];
       if (INVERSE) {
-        const R f = oo_sqrt_fast<R>(Lm);
+        const R f = oo_lambda_fast<R>(lambda, Lm);
         v.x = ((v.x * f) * f) * scale;
         v.y = ((v.y * f) * f) * scale;
       } else {
@@ -994,7 +1041,7 @@ mix_xpass_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc, 
       const R lambda = (R)(gamma + alpha * (double)sw);
       const R Lm = lambda * lambda;
       if (INVERSE) {
-        const R f = oo_sqrt_fast<R>(Lm);
+        const R f = oo_lambda_fast<R>(lambda, Lm);
         v[0].x = (v[0].x * f) * f;
         v[0].y = (v[0].y * f) * f;
       } else {
@@ -1233,6 +1280,41 @@ static int cslab_launch(bool inv, void* real, float2* spec, long long slabs, con
   return LGM_OK;
 }
 
+// Quarter-slab path (qslab.cuh): fp32, Y = Z = 256, beta == 0. Three launches, same names in the launch
+// counters as the passes they replace. LGM_NO_QSLAB (kernel experiments): the cluster slab kernels.
+template <int NX>
+static int qslab_run(float* out, const float* in, float2* spec, long long NC, const FluidPlan& p, int inverse,
+                     double alpha, double gamma, float scale, int rev0, int revx, cudaStream_t s) {
+  constexpr int Y = 256, Z = 256, YQ = Y / 4, M = Z / 2, ZC = M + 1;
+  const size_t smem_s = sizeof(float2) * ((size_t)ZC * (YQ + 1) + Z + M + YQ);
+  const size_t smem_x = sizeof(float2) * ((size_t)NX * kQxP + NX) + sizeof(float) * NX;
+  const unsigned nslab = (unsigned)(4 * NC * NX);
+  LGM_CUDA_TRY(set_smem(qslab_fwd_kernel<Y, Z>, smem_s), "qslab_fwd smem");
+  qslab_fwd_kernel<Y, Z><<<nslab, kQsThreads, smem_s, s>>>(spec, in, (const float2*)p.tw[2], (const float2*)p.tw[1], rev0);
+  count_launch("slab_fwd", s);
+  dim3 grid((unsigned)(YQ * ZC / kQxT), (unsigned)NC);
+  static_assert((YQ * ZC) % kQxT == 0, "quarter block must be a whole number of X-pass tiles");
+  if (inverse) {
+    LGM_CUDA_TRY(set_smem(xpassq_kernel<NX, YQ, true>, smem_x), "xpassq smem");
+    xpassq_kernel<NX, YQ, true><<<grid, kQxThreads, smem_x, s>>>(spec, ZC, (const float2*)p.tw[0], (const float2*)p.tw[1],
+        (const float*)p.q_lx, (const float*)p.q_wy, (const float*)p.wl[2], alpha, gamma, scale, revx);
+  } else {
+    LGM_CUDA_TRY(set_smem(xpassq_kernel<NX, YQ, false>, smem_x), "xpassq smem");
+    xpassq_kernel<NX, YQ, false><<<grid, kQxThreads, smem_x, s>>>(spec, ZC, (const float2*)p.tw[0], (const float2*)p.tw[1],
+        (const float*)p.q_lx, (const float*)p.q_wy, (const float*)p.wl[2], alpha, gamma, scale, revx);
+  }
+  count_launch("xpass", s);
+  LGM_CUDA_TRY(set_smem(qslab_inv_kernel<Y, Z>, smem_s), "qslab_inv smem");
+  qslab_inv_kernel<Y, Z><<<nslab, kQsThreads, smem_s, s>>>(out, spec, (const float2*)p.tw[2], (const float2*)p.tw[1], rev0);
+  count_launch("slab_inv", s);
+  return LGM_OK;
+}
+
+static bool qslab_enabled() {
+  static const bool on = getenv("LGM_NO_QSLAB") == nullptr;
+  return on;
+}
+
 template <typename R>
 static int slab_pass(bool inv, int Y, int Z, void* real, typename Cx<R>::T* spec, long long slabs,
                      const FluidPlan& p, int rev, cudaStream_t s) {
@@ -1294,6 +1376,20 @@ static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64
     const long long rows = g * dim * (V / nlast);
     int rc = LGM_EUNSUP;
     const int revx = alternate_passes() ? !rev0 : rev0;
+    if constexpr (sizeof(R) == 4) {
+      if (p.qslab && beta == 0.0 && qslab_enabled()) {
+        switch (X) {
+          case 64: rc = qslab_run<64>((float*)out_g, (const float*)in_g, (float2*)spec, g * dim, p, inverse, alpha, gamma, (float)scale, rev0, revx, s); break;
+          case 128: rc = qslab_run<128>((float*)out_g, (const float*)in_g, (float2*)spec, g * dim, p, inverse, alpha, gamma, (float)scale, rev0, revx, s); break;
+          case 256: rc = qslab_run<256>((float*)out_g, (const float*)in_g, (float2*)spec, g * dim, p, inverse, alpha, gamma, (float)scale, rev0, revx, s); break;
+          default: break;
+        }
+        if (rc != LGM_EUNSUP) {
+          if (rc) return rc;
+          continue;
+        }
+      }
+    }
     if (dim == 3) rc = slab_pass<R>(false, Y, nlast, (void*)in_g, spec, g * dim * X, p, rev0, s);
     const bool slab = (rc == LGM_OK);
     if (rc != LGM_OK && rc != LGM_EUNSUP) return rc;
