@@ -41,6 +41,10 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) {
       : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return r;
 }
+// v -> fl(fl(post * v) + 0): what `ds*u + dt*interp(zeros)` of the compose stage leaves (gather3.cu)
+__device__ __forceinline__ float post_scale(float post, float v) { return __fadd_rn(__fmul_rn(post, v), 0.f); }
+__device__ __forceinline__ double post_scale(double post, double v) { return __dadd_rn(__dmul_rn(post, v), 0.0); }
+
 template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
   C r;
   r.x = a.x * b.x - a.y * b.y;
@@ -666,10 +670,11 @@ __device__ __forceinline__ void real_edge_stage(typename Cx<R>::T* tile, int rs,
 // half-warp hit 16 distinct bank pairs. Forward: global -> registers -> tile; inverse: tile ->
 // registers -> global. Removes the separate fill / drain loop of the Z passes (one shared-memory
 // write + read of the whole tile). Needs L % 32 == 0. JSH / jump as in fft_stage.
-template <typename R, int M, int RAD, int L, bool INV, int JSH = 0>
+// POST (inverse only): every stored real is scaled by `post` on its way out (post_scale).
+template <typename R, int M, int RAD, int L, bool INV, int JSH = 0, bool POST = false>
 __device__ __forceinline__ void zedge_stage(typename Cx<R>::T* __restrict__ g, typename Cx<R>::T* tile, int rs,
                                             const typename Cx<R>::T* __restrict__ tw, int tid, int nth,
-                                            int jump = 0, int lstride = M) {  // lstride: words between lines
+                                            int jump = 0, int lstride = M, R post = R(1)) {  // lstride: words between lines
   using C = typename Cx<R>::T;
   constexpr int SUB = M / RAD;
   constexpr int W = SUB < 32 ? 32 / SUB : 1;   // lines per warp
@@ -707,7 +712,14 @@ __device__ __forceinline__ void zedge_stage(typename Cx<R>::T* __restrict__ g, t
       }
       reg_fft<RAD, true>(x);
 #pragma unroll
-      for (int i = 0; i < RAD; ++i) gp[bitrev(i, BITS) * SUB] = x[i];
+      for (int i = 0; i < RAD; ++i) {
+        C v = x[i];
+        if (POST) {
+          v.x = post_scale(post, v.x);
+          v.y = post_scale(post, v.y);
+        }
+        gp[bitrev(i, BITS) * SUB] = v;
+      }
     }
   }
 }
@@ -730,10 +742,10 @@ __device__ __forceinline__ void real_fft_fwd_g(const R* g, typename Cx<R>::T* ti
   }
   real_edge_stage<R, M, L, false>(tile, rs, 1, twz, tid, nth);
 }
-template <typename R, int M, int L>
+template <typename R, int M, int L, bool POST = false>
 __device__ __forceinline__ void real_fft_inv_g(R* g, typename Cx<R>::T* tile, int rs,
                                                const typename Cx<R>::T* twM, const typename Cx<R>::T* twz,
-                                               int tid, int nth, int lstride = M) {
+                                               int tid, int nth, int lstride = M, R post = R(1)) {
   using C = typename Cx<R>::T;
   constexpr int RAD0 = 1 << stage_bits(ilog2(M), 0);
   real_edge_stage<R, M, L, true>(tile, rs, 1, twz, tid, nth);
@@ -742,7 +754,7 @@ __device__ __forceinline__ void real_fft_inv_g(R* g, typename Cx<R>::T* tile, in
     ColFFT<R, M, M / RAD0, 1, L>::inv_nolast(tile, rs, 1, twM, tid, nth);
     __syncthreads();
   }
-  zedge_stage<R, M, RAD0, L, true>(reinterpret_cast<C*>(g), tile, rs, twM, tid, nth, 0, lstride);
+  zedge_stage<R, M, RAD0, L, true, 0, POST>(reinterpret_cast<C*>(g), tile, rs, twM, tid, nth, 0, lstride, post);
 }
 
 // real forward: tile rows 0..M-1 hold z[j] = (x[2j], x[2j+1]); on return rows 0..M hold the half

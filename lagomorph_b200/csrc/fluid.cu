@@ -466,10 +466,11 @@ slab_fwd_kernel(typename Cx<R>::T* __restrict__ spec, const R* __restrict__ in,
 }
 
 // Slab inverse: mirror of slab_fwd_kernel (spectrum slab -> Y real lines), unnormalised.
-template <typename R, int Y, int Z>
+template <typename R, int Y, int Z, bool POST>
 __global__ void __launch_bounds__(kFftThreads)
 slab_inv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec,
-                const typename Cx<R>::T* __restrict__ twz_g, const typename Cx<R>::T* __restrict__ twy_g, int rev) {
+                const typename Cx<R>::T* __restrict__ twz_g, const typename Cx<R>::T* __restrict__ twy_g, int rev,
+                R post) {
   const unsigned bx = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   using C = typename Cx<R>::T;
   constexpr int M = Z / 2, P = Y + 1, ZC = M + 1;
@@ -493,7 +494,7 @@ slab_inv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec,
   __syncthreads();
   if constexpr (kZEdge<M, Y>) {
     // fused unsplit stage, then the last radix stage stores straight to global memory (no drain loop)
-    real_fft_inv_g<R, M, Y>(out + (size_t)bx * Y * Z, tile, P, twM, twz, tid, kFftThreads);
+    real_fft_inv_g<R, M, Y, POST>(out + (size_t)bx * Y * Z, tile, P, twM, twz, tid, kFftThreads, M, post);
   } else {
     real_fft_inv<R, M, Y>(tile, P, 1, twM, twz, tid, kFftThreads);  // fused unsplit + inverse half-length FFT
     __syncthreads();
@@ -501,7 +502,12 @@ slab_inv_kernel(R* __restrict__ out, const typename Cx<R>::T* __restrict__ spec,
 #pragma unroll 4
     for (int idx = tid; idx < Y * M; idx += kFftThreads) {
       const int y = idx / M, j = idx % M;
-      o2[idx] = tile[j * P + y];
+      C v = tile[j * P + y];
+      if (POST) {
+        v.x = post_scale(post, v.x);
+        v.y = post_scale(post, v.y);
+      }
+      o2[idx] = v;
     }
   }
 }
@@ -847,9 +853,19 @@ xpass2_kernel(typename Cx<R>::T* __restrict__ spec, long long plane, int Zc,
       const unsigned pbx0 = (unsigned)(lin % gridDim.x), pby0 = (unsigned)(lin / gridDim.x);
       const unsigned pbx = rev ? gridDim.x - 1 - pbx0 : pbx0, pby = rev ? gridDim.y - 1 - pby0 : pby0;
       const long long pq0 = (long long)pbx * T;
-      if (plane - pq0 >= T)
-        for (int r = tid; r < NCH * NX; r += kFftThreads)
-          l2_prefetch(spec + (long long)pby * NCH * NX * plane + (long long)r * plane + pq0, (unsigned)(T * sizeof(C)));
+#ifndef LGM_PF_XPASS_MODE
+#define LGM_PF_XPASS_MODE 0  /* 0: one bulk prefetch per row; n > 0: n plain prefetch.global.L2 per row */
+#endif
+      if (plane - pq0 >= T) {
+        if (LGM_PF_XPASS_MODE == 0) {
+          for (int r = tid; r < NCH * NX; r += kFftThreads)
+            l2_prefetch(spec + (long long)pby * NCH * NX * plane + (long long)r * plane + pq0, (unsigned)(T * sizeof(C)));
+        } else {
+          constexpr int PM = LGM_PF_XPASS_MODE > 0 ? LGM_PF_XPASS_MODE : 1;
+          for (int pi = tid; pi < NCH * NX * PM; pi += kFftThreads)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(spec + (long long)pby * NCH * NX * plane + (long long)(pi / PM) * plane + pq0 + (pi % PM) * (T / PM)));
+        }
+      }
     }
   }
   // per-thread (y,z) part of the symbol
@@ -1243,7 +1259,7 @@ struct FastLaunch {
 // Slab path launchers (3-D, Y == Z in {16,32,64,128}); LGM_EUNSUP when the shape has no slab kernel.
 template <typename R, int YZ>
 static int slab_launch(bool inv, void* real, typename Cx<R>::T* spec, long long slabs, const FluidPlan& p,
-                       int rev, cudaStream_t s) {
+                       int rev, cudaStream_t s, const double* post = nullptr) {
   using C = typename Cx<R>::T;
   constexpr int M = YZ / 2;
   const size_t smem = sizeof(C) * ((size_t)(M + 1) * (YZ + 1) + YZ + M + YZ);
@@ -1252,8 +1268,13 @@ static int slab_launch(bool inv, void* real, typename Cx<R>::T* spec, long long 
     slab_fwd_kernel<R, YZ, YZ><<<(unsigned)slabs, kFftThreads, smem, s>>>(spec, (const R*)real, (const C*)p.tw[2], (const C*)p.tw[1], rev);
     count_launch("slab_fwd", s);
   } else {
-    LGM_CUDA_TRY(set_smem(slab_inv_kernel<R, YZ, YZ>, smem), "slab_inv smem");
-    slab_inv_kernel<R, YZ, YZ><<<(unsigned)slabs, kFftThreads, smem, s>>>((R*)real, spec, (const C*)p.tw[2], (const C*)p.tw[1], rev);
+    if (post) {
+      LGM_CUDA_TRY(set_smem(slab_inv_kernel<R, YZ, YZ, true>, smem), "slab_inv smem");
+      slab_inv_kernel<R, YZ, YZ, true><<<(unsigned)slabs, kFftThreads, smem, s>>>((R*)real, spec, (const C*)p.tw[2], (const C*)p.tw[1], rev, (R)*post);
+    } else {
+      LGM_CUDA_TRY(set_smem(slab_inv_kernel<R, YZ, YZ, false>, smem), "slab_inv smem");
+      slab_inv_kernel<R, YZ, YZ, false><<<(unsigned)slabs, kFftThreads, smem, s>>>((R*)real, spec, (const C*)p.tw[2], (const C*)p.tw[1], rev, R(1));
+    }
     count_launch("slab_inv", s);
   }
   return LGM_OK;
@@ -1284,7 +1305,7 @@ static int cslab_launch(bool inv, void* real, float2* spec, long long slabs, con
 // counters as the passes they replace. LGM_NO_QSLAB (kernel experiments): the cluster slab kernels.
 template <int NX>
 static int qslab_run(float* out, const float* in, float2* spec, long long NC, const FluidPlan& p, int inverse,
-                     double alpha, double gamma, float scale, int rev0, int revx, cudaStream_t s) {
+                     double alpha, double gamma, float scale, int rev0, int revx, cudaStream_t s, const double* post) {
   constexpr int Y = 256, Z = 256, YQ = Y / 4, M = Z / 2, ZC = M + 1;
   const size_t smem_s = sizeof(float2) * ((size_t)ZC * (YQ + 1) + Z + M + YQ);
   const size_t smem_x = sizeof(float2) * ((size_t)NX * kQxP + NX) + sizeof(float) * NX;
@@ -1304,8 +1325,13 @@ static int qslab_run(float* out, const float* in, float2* spec, long long NC, co
         (const float*)p.q_lx, (const float*)p.q_wy, (const float*)p.wl[2], alpha, gamma, scale, revx);
   }
   count_launch("xpass", s);
-  LGM_CUDA_TRY(set_smem(qslab_inv_kernel<Y, Z>, smem_s), "qslab_inv smem");
-  qslab_inv_kernel<Y, Z><<<nslab, kQsThreads, smem_s, s>>>(out, spec, (const float2*)p.tw[2], (const float2*)p.tw[1], rev0);
+  if (post) {
+    LGM_CUDA_TRY(set_smem(qslab_inv_kernel<Y, Z, true>, smem_s), "qslab_inv smem");
+    qslab_inv_kernel<Y, Z, true><<<nslab, kQsThreads, smem_s, s>>>(out, spec, (const float2*)p.tw[2], (const float2*)p.tw[1], rev0, (float)*post);
+  } else {
+    LGM_CUDA_TRY(set_smem(qslab_inv_kernel<Y, Z, false>, smem_s), "qslab_inv smem");
+    qslab_inv_kernel<Y, Z, false><<<nslab, kQsThreads, smem_s, s>>>(out, spec, (const float2*)p.tw[2], (const float2*)p.tw[1], rev0, 1.f);
+  }
   count_launch("slab_inv", s);
   return LGM_OK;
 }
@@ -1317,16 +1343,19 @@ static bool qslab_enabled() {
 
 template <typename R>
 static int slab_pass(bool inv, int Y, int Z, void* real, typename Cx<R>::T* spec, long long slabs,
-                     const FluidPlan& p, int rev, cudaStream_t s) {
+                     const FluidPlan& p, int rev, cudaStream_t s, const double* post = nullptr, bool* posted = nullptr) {
+  // post / posted: scale the real output on its way out (single-CTA slab kernels only); *posted says
+  // whether that happened
   if (Y != Z) return LGM_EUNSUP;
   if constexpr (sizeof(R) == 4) {
     if (Y == 256) return cslab_launch(inv, real, spec, slabs, p, rev, s);
   }
+  if (posted && inv && post && (Y == 16 || Y == 32 || Y == 64 || Y == 128)) *posted = true;
   switch (Y) {
-    case 16: return slab_launch<R, 16>(inv, real, spec, slabs, p, rev, s);
-    case 32: return slab_launch<R, 32>(inv, real, spec, slabs, p, rev, s);
-    case 64: return slab_launch<R, 64>(inv, real, spec, slabs, p, rev, s);
-    case 128: return slab_launch<R, 128>(inv, real, spec, slabs, p, rev, s);
+    case 16: return slab_launch<R, 16>(inv, real, spec, slabs, p, rev, s, post);
+    case 32: return slab_launch<R, 32>(inv, real, spec, slabs, p, rev, s, post);
+    case 64: return slab_launch<R, 64>(inv, real, spec, slabs, p, rev, s, post);
+    case 128: return slab_launch<R, 128>(inv, real, spec, slabs, p, rev, s, post);
     default: return LGM_EUNSUP;
   }
 }
@@ -1352,7 +1381,7 @@ static long long chunk_budget_bytes() {
 template <typename R>
 static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64_t* shape,
                       int inverse, double alpha, double beta, double gamma, void* ws,
-                      const FluidPlan& p, int rev0, cudaStream_t s) {
+                      const FluidPlan& p, int rev0, cudaStream_t s, const double* post, bool* posted) {
   // rev0: traversal direction of the two slab passes (0 = ascending block order); the X pass between
   // them runs the other way round so that each pass starts on what its predecessor wrote last (L2)
   using C = typename Cx<R>::T;
@@ -1379,13 +1408,14 @@ static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64
     if constexpr (sizeof(R) == 4) {
       if (p.qslab && beta == 0.0 && qslab_enabled()) {
         switch (X) {
-          case 64: rc = qslab_run<64>((float*)out_g, (const float*)in_g, (float2*)spec, g * dim, p, inverse, alpha, gamma, (float)scale, rev0, revx, s); break;
-          case 128: rc = qslab_run<128>((float*)out_g, (const float*)in_g, (float2*)spec, g * dim, p, inverse, alpha, gamma, (float)scale, rev0, revx, s); break;
-          case 256: rc = qslab_run<256>((float*)out_g, (const float*)in_g, (float2*)spec, g * dim, p, inverse, alpha, gamma, (float)scale, rev0, revx, s); break;
+          case 64: rc = qslab_run<64>((float*)out_g, (const float*)in_g, (float2*)spec, g * dim, p, inverse, alpha, gamma, (float)scale, rev0, revx, s, post); break;
+          case 128: rc = qslab_run<128>((float*)out_g, (const float*)in_g, (float2*)spec, g * dim, p, inverse, alpha, gamma, (float)scale, rev0, revx, s, post); break;
+          case 256: rc = qslab_run<256>((float*)out_g, (const float*)in_g, (float2*)spec, g * dim, p, inverse, alpha, gamma, (float)scale, rev0, revx, s, post); break;
           default: break;
         }
         if (rc != LGM_EUNSUP) {
           if (rc) return rc;
+          if (post) *posted = true;
           continue;
         }
       }
@@ -1419,7 +1449,7 @@ static int fluid_fast(void* out, const void* in, int64_t N, int dim, const int64
     }
     rc = LGM_EUNSUP;
     if (slab) {
-      rc = slab_pass<R>(true, Y, nlast, (void*)out_g, spec, g * dim * X, p, rev0, s);
+      rc = slab_pass<R>(true, Y, nlast, (void*)out_g, spec, g * dim * X, p, rev0, s, post, posted);
       if (rc == LGM_EUNSUP) {  // cluster launch refused after the forward slab ran: unfused inverse passes
         LGM_SWITCH_POW2(Y, MAXN, rc = (FL::template ypass<NN, true>(spec, (int)(g * dim), X, Zc, (const C*)p.tw[1], s)));
         if (rc) return rc;
@@ -1644,9 +1674,17 @@ static int64_t fluid_ws_bytes(int64_t N, int dim, const int64_t* shape) {
 }
 
 template <typename R>
+__global__ void __launch_bounds__(256) post_scale_kernel(R* __restrict__ x, long long total, R post) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < total) x[i] = post_scale(post, x[i]);
+}
+
+// post != nullptr: the result is additionally scaled, out <- fl(fl(*post * out) + 0) -- inside the last
+// kernel where the path has a hook for it (slab kernels), by one more elementwise launch elsewhere.
+template <typename R>
 int fluid_apply_t(void* out, const void* in, int64_t N, int dim, const int64_t* shape, int inverse,
                   double alpha, double beta, double gamma, void* ws, int64_t ws_bytes, int rev,
-                  cudaStream_t s) {
+                  cudaStream_t s, const double* post = nullptr) {
   if (N == 0) return LGM_OK;
   for (int a = 0; a < dim; ++a)
     if (shape[a] <= 0) return LGM_OK;
@@ -1656,33 +1694,43 @@ int fluid_apply_t(void* out, const void* in, int64_t N, int dim, const int64_t* 
   const FluidPlan* p = nullptr;
   int rc = get_plan<R>(dim, shape, s, &p);
   if (rc) return rc;
+  bool posted = false;
   if (p->fast) {
     if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws) & 15)
       return set_error(LGM_EINVAL, "lgm_fluid_apply: pointers must be 16-byte aligned");
-    rc = fluid_fast<R>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, *p, rev, s);
+    rc = fluid_fast<R>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, *p, rev, s, post, &posted);
   } else if (mixed_ok<R>(dim, shape)) {
     rc = fluid_mixed<R>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, *p, s);
   } else {
     rc = fluid_naive<R>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, *p, s);
   }
   if (rc) return rc;
+  if (post && !posted) {
+    long long total = N * dim;
+    for (int a = 0; a < dim; ++a) total *= shape[a];
+    post_scale_kernel<R><<<(unsigned)cdiv(total, 256), 256, 0, s>>>((R*)out, total, (R)*post);
+    count_launch("post_scale", s);
+  }
   return finish(s, "lgm_fluid_apply");
 }
 
-template int fluid_apply_t<float>(void*, const void*, int64_t, int, const int64_t*, int, double, double, double, void*, int64_t, int, cudaStream_t);
-template int fluid_apply_t<double>(void*, const void*, int64_t, int, const int64_t*, int, double, double, double, void*, int64_t, int, cudaStream_t);
-
 // lgm_fluid_apply with an explicit traversal direction (used by the EPDiff step / shoot drivers)
-int fluid_apply_dir(int dtype, void* out, const void* in, int64_t N, int dim, const int64_t* shape, int inverse,
-                    double alpha, double beta, double gamma, void* ws, int64_t ws_bytes, int rev, cudaStream_t s) {
+int fluid_apply_post(int dtype, void* out, const void* in, int64_t N, int dim, const int64_t* shape, int inverse,
+                     double alpha, double beta, double gamma, void* ws, int64_t ws_bytes, int rev, const double* post,
+                     cudaStream_t s) {
   if (dim != 2 && dim != 3) return set_error(LGM_EINVAL, "Only two- and three-dimensional fluid metric is supported");
   if (N < 0 || N > 21845) return set_error(LGM_EINVAL, "lgm_fluid_apply: batch size out of range");
   if (!(dim == 2 ? geom_fits<2>(shape) : geom_fits<3>(shape))) return set_error(LGM_EINVAL, "lgm_fluid_apply: volume too large");
   if (dtype == LGM_F32)
-    return fluid_apply_t<float>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, ws_bytes, rev, s);
+    return fluid_apply_t<float>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, ws_bytes, rev, s, post);
   if (dtype == LGM_F64)
-    return fluid_apply_t<double>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, ws_bytes, rev, s);
+    return fluid_apply_t<double>(out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, ws_bytes, rev, s, post);
   return set_error(LGM_EINVAL, "lgm_fluid_apply: unsupported dtype %d", dtype);
+}
+
+int fluid_apply_dir(int dtype, void* out, const void* in, int64_t N, int dim, const int64_t* shape, int inverse,
+                    double alpha, double beta, double gamma, void* ws, int64_t ws_bytes, int rev, cudaStream_t s) {
+  return fluid_apply_post(dtype, out, in, N, dim, shape, inverse, alpha, beta, gamma, ws, ws_bytes, rev, nullptr, s);
 }
 
 int64_t fluid_workspace_bytes(int dtype, int64_t N, int dim, const int64_t* shape) {

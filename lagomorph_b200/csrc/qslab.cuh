@@ -26,7 +26,7 @@ namespace lgm {
 #define LGM_PF_QSLAB 148  /* CTAs ahead whose input is prefetched into L2 (0 = off) */
 #endif
 #ifndef LGM_PF_XPASSQ
-#define LGM_PF_XPASSQ 0  /* X pass: tile of the CTA this many positions ahead prefetched into L2 (0 = off) */
+#define LGM_PF_XPASSQ 111  /* X pass: tile of the CTA this many positions ahead prefetched into L2 (0 = off) */
 #endif
 #ifndef LGM_XPASSQ_MINBLOCKS
 #define LGM_XPASSQ_MINBLOCKS 2
@@ -77,10 +77,10 @@ qslab_fwd_kernel(float2* __restrict__ spec, const float* __restrict__ in, const 
   ColFFT<float, YQ, YQ, 0, ZC>::template fwd_g<false, true>(tile, 1, P, twy, tid, kQsThreads, gout, gout);
 }
 
-template <int Y, int Z>
+template <int Y, int Z, bool POST>
 __global__ void __launch_bounds__(kQsThreads, 3)
 qslab_inv_kernel(float* __restrict__ out, const float2* __restrict__ spec, const float2* __restrict__ twz_g,
-                 const float2* __restrict__ twy_g, int rev) {
+                 const float2* __restrict__ twy_g, int rev, float post) {
   constexpr int YQ = Y / 4, M = Z / 2, ZC = M + 1, P = YQ + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tile = reinterpret_cast<float2*>(smem_raw);
@@ -102,7 +102,7 @@ qslab_inv_kernel(float* __restrict__ out, const float2* __restrict__ spec, const
   GSide<float2> gin{const_cast<float2*>(spec) + (slab * Y + q * YQ) * ZC, ZC, ZC};
   ColFFT<float, YQ, YQ, 0, ZC>::template inv_g<true, false>(tile, 1, P, twy, tid, kQsThreads, gin, gin);
   __syncthreads();
-  real_fft_inv_g<float, M, YQ>(out + (slab * Y + q) * Z, tile, P, twM, twz, tid, kQsThreads, 4 * M);
+  real_fft_inv_g<float, M, YQ, POST>(out + (slab * Y + q) * Z, tile, P, twM, twz, tid, kQsThreads, 4 * M, post);
 }
 
 // 4-point DFT over q (forward: w4 = -i) and its inverse, unnormalised
@@ -155,8 +155,13 @@ xpassq_kernel(float2* __restrict__ spec, int Zc, const float2* __restrict__ twx_
       const unsigned pbx0 = (unsigned)(lin % gridDim.x), pby0 = (unsigned)(lin / gridDim.x);
       const unsigned pbx = rev ? gridDim.x - 1 - pbx0 : pbx0, pby = rev ? gridDim.y - 1 - pby0 : pby0;
       const C* pb = spec + (long long)pby * NX * plane + (long long)pbx * T;
-      for (int pi = tid; pi < NX * 4; pi += kQxThreads)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (long long)(pi >> 2) * plane + (pi & 3) * QS));
+#ifndef LGM_PF_XPASSQ_SECT
+#define LGM_PF_XPASSQ_SECT 1
+#endif
+      for (int pi = tid; pi < NX * 4 * LGM_PF_XPASSQ_SECT; pi += kQxThreads) {
+        const int pc = pi / LGM_PF_XPASSQ_SECT, sc = pi % LGM_PF_XPASSQ_SECT;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (long long)(pc >> 2) * plane + (pc & 3) * QS + sc * (T / LGM_PF_XPASSQ_SECT)));
+      }
     }
   }
   __syncthreads();

@@ -19,6 +19,9 @@ int compose3_f32(void* out, const void* u, const void* v, int64_t N, const int64
                  int rev, cudaStream_t s);
 int fluid_apply_dir(int dtype, void* out, const void* in, int64_t N, int dim, const int64_t* shape, int inverse,
                     double alpha, double beta, double gamma, void* ws, int64_t ws_bytes, int rev, cudaStream_t s);
+int fluid_apply_post(int dtype, void* out, const void* in, int64_t N, int dim, const int64_t* shape, int inverse,
+                     double alpha, double beta, double gamma, void* ws, int64_t ws_bytes, int rev, const double* post,
+                     cudaStream_t s);
 
 template <typename R>
 __global__ void mul_mask2_kernel(R* __restrict__ m, const R* __restrict__ mask, long long total) {
@@ -27,6 +30,16 @@ __global__ void mul_mask2_kernel(R* __restrict__ m, const R* __restrict__ mask, 
 }
 
 static size_t align_up256(size_t v) { return (v + 255) / 256 * 256; }
+
+// First step from the identity (phiinv_in == NULL, no mask): Ad_star(0, m0) = m0 and
+// compose_disp_vel(0, v, -dt) = -dt*v, so the step is ONE sharp whose last kernel scales its output
+// by -dt (fl(fl(-dt * v) + 0), the compose stage's own rounding): 3 launches instead of 5, no memset,
+// 24 B per voxel instead of 96. Same bits as the full step except the sign of exact zeros (the full
+// step turns -0 into +0). LGM_NO_FIRST_STEP_SHORTCUT=1: the full step (kernel experiments, tests).
+static bool first_step_shortcut() {
+  static const bool on = getenv("LGM_NO_FIRST_STEP_SHORTCUT") == nullptr;
+  return on;
+}
 
 static bool alternate_enabled() {
   static const bool on = getenv("LGM_NO_ALTERNATE") == nullptr;  // kernel experiments
@@ -76,7 +89,8 @@ extern "C" int lgm_expmap_fwd(int dtype, void* phiinv_out, const void* phiinv_in
 
   // the steps ping-pong between phiinv_out and tmp so that the last one lands in phiinv_out
   const void* cur = phiinv_in;
-  if (!cur) {  // phiinv = zeros (lddmm.py:84-85)
+  const bool shortcut = !phiinv_in && !mommask && first_step_shortcut();
+  if (!cur && !shortcut) {  // phiinv = zeros (lddmm.py:84-85)
     void* z = (num_steps & 1) ? tmp : phiinv_out;
     cudaError_t e = cudaMemsetAsync(z, 0, field_bytes, s);
     if (e != cudaSuccess) return set_error((int)e, "lgm_expmap_fwd: memset: %s", cudaGetErrorString(e));
@@ -91,6 +105,14 @@ extern "C" int lgm_expmap_fwd(int dtype, void* phiinv_out, const void* phiinv_in
     // every step because compose(p) leaves the far end of phiinv for the next step's Ad_star.
     const int p = alt ? (k & 1) : 0;
     int rc = LGM_EUNSUP;
+    if (k == 0 && shortcut) {
+      // slab passes ascending: the next step's Ad_star (direction 1) starts on what was written last
+      const double post = -dt;
+      rc = fluid_apply_post(dtype, dst, m0, N, dim, shape, 1, alpha, beta, gamma, ws, ws_bytes, 0, &post, s);
+      if (rc) return rc;
+      cur = dst;
+      continue;
+    }
     if (fast3) rc = Ad_star3_f32(m, cur, m0, N, shape, p, s);
     if (rc == LGM_EUNSUP) rc = lgm_Ad_star_fwd(dtype, m, cur, m0, N, dim, shape, stream);
     if (rc) return rc;

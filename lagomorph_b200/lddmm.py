@@ -90,11 +90,24 @@ def _fused_bwd_ok(metric, m0, phiinv, mommask):
     return int(L.lib.lgm_epdiff_bwd_scratch_bytes(L.dtype_code(m0), m0.shape[0], 3, L.shape_arr(m0.shape[2:]))) >= 0
 
 
-def _steps_saving(metric, m0, dt, N, phiinv, mommask):
-    """N forward steps keeping each step's input displacement and velocity (what the backward reads)."""
+def _identity_shortcut():
+    return os.environ.get("LGM_NO_FIRST_STEP_SHORTCUT") is None
+
+
+def _steps_saving(metric, m0, dt, N, phiinv, mommask, from_identity=False):
+    """N forward steps keeping each step's input displacement and velocity (what the backward reads).
+    from_identity: phiinv is the all-zero field expmap made for phiinv=None; the first step is then
+    Ad_star(0, m0) = m0, compose_disp_vel(0, v, -dt) = -dt*v: one sharp and a scaling (as lgm_expmap_fwd
+    does, csrc/shoot3.cu), and its backward is a scaling and one sharp (_steps_backward)."""
     phis, vs = [], []
     with torch.no_grad():
         for n in range(N):
+            if n == 0 and from_identity:
+                v = metric.sharp(m0 if mommask is None else m0 * mommask)
+                phis.append(phiinv)
+                vs.append(phiinv)       # placeholder: the shortcut backward reads neither
+                phiinv = v.mul_(-dt)
+                continue
             m = adjrep.Ad_star(phiinv, m0)
             if mommask is not None:
                 m = m * mommask
@@ -105,7 +118,7 @@ def _steps_saving(metric, m0, dt, N, phiinv, mommask):
     return phiinv, phis, vs
 
 
-def _steps_backward(metric, m0, dt, phis, vs, mommask, gradout, need_m0, need_phi):
+def _steps_backward(metric, m0, dt, phis, vs, mommask, gradout, need_m0, need_phi, from_identity=False):
     """Backward of the steps recorded by _steps_saving, last step first: one lgm_epdiff_step_bwd per
     step; dL/dm0 accumulates in place over the steps, dL/dphiinv is carried in `g`."""
     dev = m0.device
@@ -122,6 +135,14 @@ def _steps_backward(metric, m0, dt, phis, vs, mommask, gradout, need_m0, need_ph
             want_phi = need_phi or k > 0
             if not (want_phi or need_m0):
                 break
+            if k == 0 and from_identity and not need_phi:
+                # phi_1 = -dt * sharp(m0 * mask): d_m0 += mask * sharp(-dt * g) (sharp is self-adjoint)
+                with torch.no_grad():
+                    w = metric.sharp(g.mul_(-dt))
+                    if mommask is not None:
+                        w.mul_(mommask)
+                    d_m0.add_(w)
+                break
             L.check(L.lib.lgm_epdiff_step_bwd(code, L.ptr(g), L.ptr(d_m0), L.ptr(acc), L.ptr(phis[k]), L.ptr(vs[k]),
                                               L.ptr(m0), L.ptr(mommask), N, 3, sh, float(dt), alpha, beta, gamma,
                                               L.ptr(scratch), nbytes, int(want_phi), int(need_m0),
@@ -135,12 +156,13 @@ class EPDiffShootFunction(torch.autograd.Function):
     checkpointing, the working form of lddmm.py:47-70)."""
 
     @staticmethod
-    def forward(ctx, metric, m0, dt, N, phiinv, mommask, save):
+    def forward(ctx, metric, m0, dt, N, phiinv, mommask, save, from_identity=False):
         m0c, pc = L.aligned(m0.detach()), L.aligned(phiinv.detach())
         mk = None if mommask is None else mommask.detach().contiguous()
         ctx.metric, ctx.dt, ctx.N, ctx.save, ctx.mk = metric, dt, N, save, mk
+        ctx.from_identity = bool(from_identity) and _identity_shortcut()
         if save:
-            out, phis, vs = _steps_saving(metric, m0c, dt, N, pc, mk)
+            out, phis, vs = _steps_saving(metric, m0c, dt, N, pc, mk, ctx.from_identity)
             ctx.nsaved = len(phis)
             ctx.save_for_backward(m0c, *phis, *vs)
         else:
@@ -160,9 +182,10 @@ class EPDiffShootFunction(torch.autograd.Function):
             vs = list(ctx.saved_tensors[1 + ctx.nsaved:])
         else:
             m0c, pc = ctx.saved_tensors
-            _, phis, vs = _steps_saving(ctx.metric, m0c, ctx.dt, ctx.N, pc, ctx.mk)
-        d_m0, d_phi = _steps_backward(ctx.metric, m0c, ctx.dt, phis, vs, ctx.mk, gradout, need_m0, need_phi)
-        return None, d_m0, None, None, d_phi, None, None
+            _, phis, vs = _steps_saving(ctx.metric, m0c, ctx.dt, ctx.N, pc, ctx.mk, ctx.from_identity)
+        d_m0, d_phi = _steps_backward(ctx.metric, m0c, ctx.dt, phis, vs, ctx.mk, gradout, need_m0, need_phi,
+                                      ctx.from_identity)
+        return None, d_m0, None, None, d_phi, None, None, None
 
 
 def EPDiff_step(metric, m0, dt, phiinv, mommask=None):
@@ -233,12 +256,13 @@ def expmap(metric, m0, T=1.0, num_steps=10, phiinv=None, mommask=None, checkpoin
         if num_steps > 0 and _fusable(metric, m0, m0 if phiinv is None else phiinv, mommask):
             mk = None if mommask is None else mommask.contiguous()
             return _fused_shoot(metric, L.aligned(m0), dt, num_steps, None if phiinv is None else L.aligned(phiinv), mk)
+    from_identity = phiinv is None
     if phiinv is None:
         phiinv = torch.zeros_like(m0)
     if checkpoints is None or checkpoints is False:
         if (num_steps > 0 and _needs_grad(m0, phiinv) and not _needs_grad(mommask)
                 and _fused_bwd_ok(metric, m0, phiinv, mommask)):
-            return EPDiffShootFunction.apply(metric, m0, dt, num_steps, phiinv, mommask, True)
+            return EPDiffShootFunction.apply(metric, m0, dt, num_steps, phiinv, mommask, True, from_identity)
         for i in range(num_steps):
             phiinv = EPDiff_step(metric, m0, dt, phiinv, mommask=mommask)
         return phiinv

@@ -135,6 +135,28 @@ def test_fused_backward_default_phiinv_and_loss(lm, monkeypatch):
     assert relerr(gr[0], gr[1]) <= 1e-4
 
 
+@pytest.mark.parametrize("steps", [1, 2, 4])
+@pytest.mark.parametrize("masked", [False, True])
+def test_identity_start_shortcut_gradient(lm, monkeypatch, steps, masked):
+    """phiinv=None: the first step runs as sharp + scaling and its backward as scaling + sharp
+    (lddmm._steps_saving / _steps_backward). Output and d_m0 against the per-operator autograd chain."""
+    _, m0, _, gout = make_inputs(2, (16, 16, 32), 91)
+    gm = lm.FluidMetric(PARAMS)
+    mask = None
+    if masked:
+        mask = (torch.rand(m0.shape, generator=torch.Generator().manual_seed(6)) > 0.3).float().cuda()
+    res = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("LGM_FUSED_BWD", fused)
+        a = m0.cuda().requires_grad_(True)
+        h = lm.expmap(gm, a, num_steps=steps, mommask=mask)
+        assert (type(h.grad_fn).__name__ == "EPDiffShootFunctionBackward") == (fused == "1")
+        (g,) = torch.autograd.grad(h, [a], gout.cuda())
+        res.append((h.detach(), g))
+    assert relerr(res[0][0], res[1][0]) <= 1e-5
+    assert relerr(res[0][1], res[1][1]) <= 1e-4
+
+
 def test_unsupported_shapes_fall_back(lm):
     """Z not a multiple of 32, 2-D and fp64 keep the per-operator autograd chain (still CUDA)."""
     gm = lm.FluidMetric(PARAMS)

@@ -124,3 +124,95 @@ def test_ring_compose_bit_identical_to_planar_gather(tmp_path):
     assert res["ring"].keys() == res["planar"].keys() and len(res["ring"]) == 10
     for k in res["ring"]:
         assert torch.equal(res["ring"][k], res["planar"][k]), k
+
+
+_SHORTCUT_SCRIPT = """
+import sys, torch
+sys.path.insert(0, sys.argv[2])
+import lagomorph_b200 as lm
+outs = {}
+g = torch.Generator().manual_seed(9)
+for name, sh, params, steps in (("c128", (2, 3, 128, 128, 128), [0.1, 0.0, 0.01], 3),
+                                ("q256", (1, 3, 64, 256, 256), [0.1, 0.0, 0.01], 2),
+                                ("beta", (2, 3, 32, 32, 32), [0.1, 0.01, 0.001], 3),
+                                ("odd", (1, 3, 24, 20, 36), [0.1, 0.0, 0.01], 2),
+                                ("2d", (3, 2, 64, 64), [0.1, 0.0, 0.01], 4),
+                                ("f64", (1, 3, 16, 16, 16), [0.1, 0.0, 0.01], 2)):
+    dt = torch.float64 if name == "f64" else torch.float32
+    m0 = torch.randn(sh, generator=g, dtype=dt).cuda()
+    met = lm.FluidMetric(params)
+    m0 = m0 * (3.0 / met.sharp(m0).abs().max())
+    outs[name] = lm.expmap(met, m0, num_steps=steps).cpu()
+    outs[name + "_1"] = lm.expmap(met, m0, num_steps=1).cpu()
+torch.save(outs, sys.argv[1])
+"""
+
+
+def test_first_step_shortcut_bit_identical(tmp_path):
+    """lgm_expmap_fwd from the identity runs its first step as ONE sharp with the -dt scaling in the last
+    kernel (csrc/shoot3.cu). Same bits as the full step (LGM_NO_FIRST_STEP_SHORTCUT=1, read once per
+    process: two subprocesses) on every FFT path: 128^2 slabs, quarter slabs, beta != 0, mixed radix, 2-D,
+    fp64 -- up to the sign of exact zeros, hence the comparison with ==."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "shortcut.py"
+    script.write_text(_SHORTCUT_SCRIPT)
+    res = {}
+    for tag, env in (("short", {}), ("full", {"LGM_NO_FIRST_STEP_SHORTCUT": "1"})):
+        out = str(tmp_path / (tag + ".pt"))
+        e = dict(os.environ)
+        e.pop("LGM_NO_FIRST_STEP_SHORTCUT", None)
+        e.update(env)
+        subprocess.check_call([sys.executable, str(script), out, root], env=e)
+        res[tag] = torch.load(out)
+    assert res["short"].keys() == res["full"].keys() and len(res["short"]) == 12
+    for k in res["short"]:
+        a, b = res["short"][k], res["full"][k]
+        assert torch.isfinite(a).all() and a.abs().max() > 0, k
+        assert bool((a == b).all()), k
+
+
+_QSLAB_SCRIPT = """
+import sys, torch
+sys.path.insert(0, sys.argv[2])
+import lagomorph_b200 as lm
+outs = {}
+g = torch.Generator().manual_seed(13)
+met = lm.FluidMetric([0.1, 0.0, 0.01])
+for X in (64, 128, 256):
+    m = torch.randn((1, 3, X, 256, 256), generator=g).cuda()
+    outs["sharp%d" % X] = met.sharp(m).cpu()
+    outs["flat%d" % X] = met.flat(m).cpu()
+    if X == 64:
+        outs["roundtrip_err"] = ((met.flat(met.sharp(m)) - m).norm() / m.norm()).cpu()
+torch.save(outs, sys.argv[1])
+"""
+
+
+def test_quarter_slab_path_matches_cluster_path(tmp_path):
+    """256 x 256 planes, beta == 0: the quarter-slab kernels (csrc/qslab.cuh: Y split 4 x 64, radix-4 Y
+    stage inside the X pass) against the cluster slab kernels they replace (LGM_NO_QSLAB=1), X = 64, 128,
+    256. Different factorisations of the same transform: equal to fp32 round-off (1e-6 relative L2; both
+    are checked against the CPU oracle at 1e-5 in test_fullsize_gpu.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "qslab.py"
+    script.write_text(_QSLAB_SCRIPT)
+    res = {}
+    for tag, env in (("qslab", {}), ("cluster", {"LGM_NO_QSLAB": "1"})):
+        out = str(tmp_path / (tag + ".pt"))
+        e = dict(os.environ)
+        e.pop("LGM_NO_QSLAB", None)
+        e.update(env)
+        subprocess.check_call([sys.executable, str(script), out, root], env=e)
+        res[tag] = torch.load(out)
+    for k in res["qslab"]:
+        if k == "roundtrip_err":
+            assert res["qslab"][k].item() <= 5e-5
+            continue
+        a, b = res["qslab"][k], res["cluster"][k]
+        assert ((a - b).norm() / b.norm()).item() <= 1e-6, k
