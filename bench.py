@@ -39,6 +39,23 @@ WORKLOADS = {
 }
 PARAMS = [0.1, 0.0, 0.01]           # FluidMetric used by the atlas builder (lddmm.py:213)
 ALG_BYTES_PER_VOXEL_STEP = 96       # Ad*(36) + sharp(24) + compose(36), fp32 3-D
+# A shoot from the identity (phiinv=None, what expmap and the atlas builder do) runs its FIRST step as one
+# sharp with the -dt scaling inside (csrc/shoot3.cu: Ad_star(0, m0) = m0, compose(0, v) = -dt v): that
+# step's compulsory traffic is read m0 + write phiinv = 24 B per voxel, and the roofline fractions below
+# count it as 24 B, not 96 (forward + backward: 24 + 36 instead of 324). `value` stays the plain metric,
+# N * V * num_steps / time. LGM_NO_FIRST_STEP_SHORTCUT=1 runs the full first step.
+FIRST_STEP_SHORTCUT = os.environ.get("LGM_NO_FIRST_STEP_SHORTCUT") is None
+FIRST_STEP_BYTES = 24 if FIRST_STEP_SHORTCUT else 96
+FIRST_STEP_FWD_BWD_BYTES = 60 if FIRST_STEP_SHORTCUT else 324
+
+
+def shoot_bytes_per_voxel(nsteps):
+    """algorithmic bytes per voxel of a whole forward shoot from the identity"""
+    return FIRST_STEP_BYTES + ALG_BYTES_PER_VOXEL_STEP * (nsteps - 1)
+
+
+def shoot_fwd_bwd_bytes_per_voxel(nsteps):
+    return FIRST_STEP_FWD_BWD_BYTES + 324 * (nsteps - 1)
 
 
 def peaks():
@@ -223,7 +240,7 @@ def bench_c3_atlas(torch, dist, lm, dev, world, rank, hbm, barrier, reduce_max, 
     vs = S * n ** 3 * 5 / (ms * 1e-3)
     out = {"value": S / (ms * 1e-3), "unit": "subjects/s", "ms_per_epoch": ms, "n_gpus": world,
            "voxel_steps_per_s_fwd_bwd": vs,
-           "hbm_roofline_frac_324B": vs / world * FWD_BWD_BYTES_PER_VOXEL_STEP / 1e9 / hbm,
+           "hbm_roofline_frac_324B": vs / world * (shoot_fwd_bwd_bytes_per_voxel(5) / 5) / 1e9 / hbm,
            "collective": "NCCL all_reduce of the %d MiB atlas gradient (async, overlapping the momentum update) "
                          "+ one all_reduce of 2 scalars, inside the timed region" % (n ** 3 * 4 >> 20) if world > 1
                          else "none (1 rank)",
@@ -256,7 +273,7 @@ def bench_c2_fwd_bwd(torch, lm, dev, hbm, metric, barrier, reduce_max, K=3, W=1,
     del b
     torch.cuda.empty_cache()
     return {"value": vs, "unit": "voxel-steps/s fwd+bwd", "ms_per_iteration": ms,
-            "hbm_roofline_frac_324B": vs * FWD_BWD_BYTES_PER_VOXEL_STEP / 1e9 / hbm,
+            "hbm_roofline_frac_324B": vs * (shoot_fwd_bwd_bytes_per_voxel(steps) / steps) / 1e9 / hbm,
             "config": {"shape": [n, n, n], "batch": batch, "epdiff_steps": steps}}
 
 
@@ -541,7 +558,6 @@ def main():
     dom = max(ks, key=lambda k: ks[k]["ms"]) if ks else None
     roofline = None
     breakdown = {}
-    passes_per_step = {"ypass": 2}
     for k, v in ks.items():
         per_launch_ms = v["ms"] / v["launches"]
         ab = alg_bytes(k, shape)
@@ -550,7 +566,7 @@ def main():
                  "share": v["ms"] / sum(x["ms"] for x in ks.values())}
         if ab is not None:
             # algorithmic bytes of all launches of this kernel in the profiled shoots / their total time
-            total_bytes = ab * batch * V * passes_per_step.get(k, 1) * nsteps * main_res["kernel_reps"]
+            total_bytes = ab * batch * V * v["launches"]   # every launch processes the whole batch
             entry["achieved_gbs"] = total_bytes / (v["ms"] * 1e-3) / 1e9
             entry["frac"] = entry["achieved_gbs"] / hbm
             entry["alg_bytes_per_launch"] = total_bytes / v["launches"]
@@ -568,7 +584,7 @@ def main():
                     "traffic_source": "profiles/%s (ncu --set full)" % tname if traffic else None,
                     "algorithmic_bytes_per_launch": breakdown[dom].get("alg_bytes_per_launch"),
                     "peak_source": peak_src, "algorithmic_bytes_per_voxel": alg_bytes(dom, shape)}
-    step_frac = main_res["value"] / world * ALG_BYTES_PER_VOXEL_STEP / 1e9 / hbm
+    step_frac = main_res["value"] / world * (shoot_bytes_per_voxel(nsteps) / nsteps) / 1e9 / hbm
 
     def reduce_max(ms):
         t = torch.tensor([ms], device=dev)
@@ -589,7 +605,7 @@ def main():
         def c3_shoot():
             r3 = measure("c3", max(2, args.steps // 2), 2, with_e2e=False)
             return {"value": r3["value"], "unit": "voxel-steps/s", "ms_per_step": r3["ms_per_step"],
-                    "hbm_roofline_frac_96B": r3["value"] / world * ALG_BYTES_PER_VOXEL_STEP / 1e9 / hbm,
+                    "hbm_roofline_frac_96B": r3["value"] / world * (shoot_bytes_per_voxel(r3["nsteps"]) / r3["nsteps"]) / 1e9 / hbm,
                     "kernel_ms_per_epdiff_step": {k: v["ms"] / (r3["kernel_reps"] * r3["nsteps"]) for k, v in r3["kernels"].items()},
                     "config": {"shape": list(r3["shape"]), "batch_per_gpu": r3["batch"], "epdiff_steps": r3["nsteps"]}}
         also("c3_256", c3_shoot)
@@ -615,8 +631,11 @@ def main():
                        "l2": "inputs larger than L2 (%d MiB per field vs 126 MB)" % (batch * 3 * V * 4 >> 20),
                        "parallelism": "subjects sharded over ranks, no data-path collective",
                        "host_numa_node": numa, "host_numa_note": numa_why,
-                       "momenta": "white noise low-passed by a sigma=4 Gaussian, max|sharp(m0)| = 4 voxels (BASELINE.md 4)"},
+                       "momenta": "white noise low-passed by a sigma=4 Gaussian, max|sharp(m0)| = 4 voxels (BASELINE.md 4)",
+                       "first_step": ("from the identity: one sharp with the -dt scaling inside, counted as 24 B/voxel "
+                                      "(not 96) in hbm_roofline_frac_96B" if FIRST_STEP_SHORTCUT else "full step")},
             "hbm_roofline_frac_96B": step_frac,
+            "alg_bytes_per_voxel_shoot": shoot_bytes_per_voxel(nsteps),
             "roofline": roofline, "kernel_breakdown": breakdown, "cpu_baseline": cpu,
             "e2e": main_res.get("e2e"), "gpu_launches": main_res["launches"], "clocks": main_res["clocks"],
         }

@@ -1,0 +1,183 @@
+// adstar_ring.cu -- Ad_star (out_c = sum_d (D_d phi_c + delta_cd) * m_d(x + phi(x)), adjrep.py:86-97) with
+// the STENCIL operand phi staged in shared memory by bulk asynchronous copies (cp.async.bulk + mbarrier,
+// the TMA engine), same marching scheme as compose_ring.cu.
+//
+// Why: gather3_kernel<0> is bound by L1 wavefronts. Of its ~79 wavefronts per 32 voxels, 27-30 are the
+// 21 loads of phi: the 3 centre values and their 18 stencil neighbours, where every z+-1 neighbour is an
+// unaligned 128-byte run (two cache lines = two wavefronts) and every x+-1 row misses L1. From shared
+// memory each of the 21 reads is one wavefront whatever its alignment, nothing of phi passes through
+// L1 (which is left to the m0 gather), and the centre values no longer gate a chunk with a DRAM round
+// trip. A CTA owns TY y rows x all z of XS consecutive x slabs and marches along x with a ring of 4 x
+// planes of phi (rows y-1 .. y+TY, 3 channels): while slab x is worked on from planes x-1, x, x+1,
+// plane x+2 streams in. The m0 gather (displacements of several voxels) stays the L1 gather of
+// gather3.cu. Arithmetic and evaluation order are those of gather3_kernel<0>: results are bit-identical.
+#include <cstdlib>
+#include "gather_common.cuh"
+#include "ring_common.cuh"
+
+#ifndef LGM_ARING_XS
+#define LGM_ARING_XS 16  /* x slabs marched by one CTA */
+#endif
+#ifndef LGM_ARING_PF
+#define LGM_ARING_PF 2   /* L2 prefetch of the m0 rows of this tile this many slabs ahead (0 = off) */
+#endif
+#ifndef LGM_ARING_MINB
+#define LGM_ARING_MINB 3
+#endif
+
+namespace lgm {
+
+namespace {
+
+constexpr int kARing = 4;
+
+// WPR warps share one z row (Z = 128 * WPR for Z > 128), a CTA of 8 warps covers TY = 8 / WPR rows;
+// NV chunks of 32 per thread; blockDim = (32, 8). Z = 32 * NV * WPR is a compile-time constant.
+template <int NV, int WPR>
+__global__ void __launch_bounds__(256, LGM_ARING_MINB)
+adstar_ring_kernel(float* __restrict__ out, const float* __restrict__ phi, const float* __restrict__ m, int X, int Y,
+                   int rev) {
+  constexpr int TY = 8 / WPR, ROWS = TY + 2, Z = 32 * NV * WPR;
+  extern __shared__ __align__(128) unsigned char aring_raw[];
+  float* ring = reinterpret_cast<float*>(aring_raw);                 // [kARing][3][ROWS][Z]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)kARing * 3 * ROWS * Z);
+  const int lane = threadIdx.x, w = threadIdx.y, tid = w * 32 + lane;
+  const unsigned bxi = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const unsigned byi = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int n = blockIdx.z;
+  const int y0t = byi * TY, yb = y0t - 1;
+  const int j = y0t + w / WPR;
+  const int zoff = (w % WPR) * (32 * NV);
+  const int xs0 = bxi * LGM_ARING_XS, xs1 = min(X, xs0 + LGM_ARING_XS);  // slabs [xs0, xs1)
+  const int sy = Z, sx = Y * Z;
+  const int V = X * sx;
+  const int ylo = max(yb, 0), yhi = min(y0t + TY, Y - 1);             // staged rows of every plane
+  const unsigned plane_bytes = (unsigned)((yhi - ylo + 1) * Z * 4);
+  constexpr int CH = ROWS * Z;                                         // channel stride inside a ring slot
+  const float* pn = phi + (size_t)n * 3 * V;
+  const float* bn = m + (size_t)n * 3 * V;
+  const float* bn1 = bn + V;
+  const float* bn2 = bn1 + V;
+  float* on = out + (size_t)n * 3 * V;
+  asm volatile("" : "+l"(bn), "+l"(bn1), "+l"(bn2));
+  const unsigned four = opaque_four();
+  const float hiX = (float)X - 0.5f, hiY = (float)Y - 0.5f, hiZ = (float)Z - 0.5f;
+  const int plo = max(xs0 - 1, 0), phi_ = min(xs1, X - 1);            // planes this CTA ever needs
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kARing; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int p) {  // one thread: plane p of the three channels -> ring slot p % kARing
+    if (p < plo || p > phi_) return;
+    const int slot = p & (kARing - 1);
+    mbar_expect_tx(&full[slot], 3 * plane_bytes);
+    float* dst = ring + (size_t)slot * 3 * CH + (ylo - yb) * Z;
+    const float* src = pn + (size_t)p * sx + (size_t)ylo * Z;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) bulk_g2s(dst + c * CH, src + (size_t)c * V, plane_bytes, &full[slot]);
+  };
+  if (tid == 0) {
+    issue(xs0 - 1);
+    issue(xs0);
+    issue(xs0 + 1);
+  }
+  unsigned phase = 0;  // parity to wait for, per slot
+  int waited = plo - 1;
+  const bool rowok = j < Y;
+  const float fj = (float)j;
+  // ring row offsets of this thread's y row and its clamped y neighbours (diff.h: clamped indices)
+  const int rj = (j - yb) * Z;
+  const int rjm = (j > 0) ? rj - Z : rj, rjp = (j < Y - 1) ? rj + Z : rj;
+
+  for (int x = xs0; x < xs1; ++x) {
+    __syncthreads();  // slab x-1 is done everywhere: the slot of plane x-2 may be overwritten by plane x+2
+    if (tid == 0) issue(x + 2);  // look-ahead (planes up to xs0+1 were issued in the prologue)
+    if (LGM_ARING_PF > 0 && tid >= 32 && tid < 35 && x + LGM_ARING_PF < xs1 && y0t + TY <= Y) {
+      // the undisplaced rows of m0 for slab x + LGM_ARING_PF (where most of its gather lands) -> L2
+      const float* src = bn + (size_t)(tid - 32) * V + (size_t)(x + LGM_ARING_PF) * sx + (size_t)y0t * Z;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((unsigned)(TY * Z * 4)) : "memory");
+    }
+    const int need = min(x + 1, phi_);
+    while (waited < need) {
+      ++waited;
+      const int slot = waited & (kARing - 1);
+      mbar_wait(&full[slot], (phase >> slot) & 1u);
+      phase ^= 1u << slot;
+    }
+    if (!rowok) continue;
+    const float fi = (float)x;
+    const int row0 = x * sx + j * sy;
+    const float* sc = ring + (x & (kARing - 1)) * 3 * CH;                               // plane x
+    const float* sm = (x > 0) ? ring + ((x - 1) & (kARing - 1)) * 3 * CH : sc;          // plane x-1 (clamped)
+    const float* sp = (x < X - 1) ? ring + ((x + 1) & (kARing - 1)) * 3 * CH : sc;      // plane x+1 (clamped)
+#pragma unroll
+    for (int c4 = 0; c4 < NV; ++c4) {
+      const int k = zoff + c4 * 32 + lane;
+      const int c0 = row0 + k;
+      const float A0 = sc[rj + k], A1 = sc[CH + rj + k], A2 = sc[2 * CH + rj + k];
+      const float hx = __fadd_rn(fi, A0);  // dt == 1: the double sum is exact before rounding
+      const float hy = __fadd_rn(fj, A1);
+      const float hz = __fadd_rn((float)k, A2);
+      const Ax3 ax = axis_fwd(hx, X, hiX), ay = axis_fwd(hy, Y, hiY), az = axis_fwd(hz, Z, hiZ);
+      int zs;
+      float wv;
+      z_pair(az, Z, zs, wv);
+      const unsigned rx0 = ax.i0 * sx + zs, rx1 = ax.i1 * sx + zs;
+      const unsigned ry0 = ay.i0 * sy, ry1 = ay.i1 * sy;
+      const unsigned i00 = rx0 + ry0, i01 = rx0 + ry1, i10 = rx1 + ry0, i11 = rx1 + ry1;
+      const float omt = 1.f - ax.t, omu = 1.f - ay.t, omv = 1.f - wv;
+      const float m0v = trilerp(bn, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv, four);
+      const float m1v = trilerp(bn1, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv, four);
+      const float m2v = trilerp(bn2, i00, i01, i10, i11, ax.t, ay.t, wv, omt, omu, omv, four);
+      const int kp = (k < Z - 1) ? k + 1 : k, km = (k > 0) ? k - 1 : k;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float g0 = 0.5f * (sp[c * CH + rj + k] - sm[c * CH + rj + k]);
+        float g1 = 0.5f * (sc[c * CH + rjp + k] - sc[c * CH + rjm + k]);
+        float g2 = 0.5f * (sc[c * CH + rj + kp] - sc[c * CH + rj + km]);
+        if (c == 0) g0 += 1.f;
+        if (c == 1) g1 += 1.f;
+        if (c == 2) g2 += 1.f;
+        on[c0 + (size_t)c * V] = g0 * m0v + g1 * m1v + g2 * m2v;  // diff.cu:118-120
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// LGM_EUNSUP when the ring kernel does not apply (caller uses the planar gather kernel)
+int Ad_star3_ring_f32(void* out, const void* phi, const void* m, int64_t N, const int64_t* sh, int rev,
+                      cudaStream_t s) {
+  static const bool off = getenv("LGM_NO_ADSTAR_RING") != nullptr;  // kernel experiments
+  const int64_t X = sh[0], Y = sh[1], Z = sh[2];
+  if (off || X < 4 || Y < 2 || N > 65535 || X * Y * Z >= (1LL << 31) / 4) return LGM_EUNSUP;
+  // Z = 256 (two warps per row, 4 rows + 2 halo rows per CTA) measured SLOWER than the planar kernel on
+  // B200 (1.67 vs 1.54 ms at 8 x 256^3; Z = 128: 0.368 vs 0.398 ms at 16 x 128^3): rows up to 128 only
+  static const bool z256 = getenv("LGM_ADSTAR_RING_256") != nullptr;
+  if (!(Z == 32 || Z == 64 || Z == 128 || (Z == 256 && z256))) return LGM_EUNSUP;
+  if (((uintptr_t)phi & 15) != 0) return LGM_EUNSUP;  // bulk copies need 16-byte aligned rows
+  const int wpr = Z == 256 ? 2 : 1, TY = 8 / wpr;
+  const size_t smem = (size_t)kARing * 3 * (TY + 2) * Z * 4 + kARing * 8;
+  dim3 grid((unsigned)cdiv(X, LGM_ARING_XS), (unsigned)cdiv(Y, TY), (unsigned)N), block(32, 8);
+#define LGM_ARING(NV_, WPR_)                                                                                        \
+  do {                                                                                                              \
+    cudaError_t e = cudaFuncSetAttribute(adstar_ring_kernel<NV_, WPR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem);                                                                \
+    if (e != cudaSuccess) return set_error((int)e, "Ad_star ring smem: %s", cudaGetErrorString(e));                 \
+    adstar_ring_kernel<NV_, WPR_><<<grid, block, smem, s>>>((float*)out, (const float*)phi, (const float*)m, (int)X, \
+                                                            (int)Y, rev);                                           \
+  } while (0)
+  if (Z == 32) LGM_ARING(1, 1);
+  else if (Z == 64) LGM_ARING(2, 1);
+  else if (Z == 128) LGM_ARING(4, 1);
+  else LGM_ARING(4, 2);
+#undef LGM_ARING
+  count_launch("Ad_star", s);
+  return finish(s, "lgm_Ad_star_fwd(ring)");
+}
+
+}  // namespace lgm

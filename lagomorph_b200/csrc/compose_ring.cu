@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 #include "gather_common.cuh"
+#include "ring_common.cuh"
 
 #ifndef LGM_RING_XS
 #define LGM_RING_XS 16  /* x slabs marched by one CTA */
@@ -32,29 +33,6 @@ namespace {
 
 constexpr int kRing = 4;
 constexpr unsigned kFullMask = 0xffffffffu;
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-  } while (!ok);
-}
 
 // WPR warps share one z row (Z = 128 * WPR for Z > 128), a CTA of 8 warps covers TY = 8 / WPR rows;
 // NV chunks of 32 per thread. blockDim = (32, 8).

@@ -374,8 +374,15 @@ static bool fast3_ok(const void* p0, const void* p1, const void* p2, int64_t N, 
 }
 
 // returns LGM_EUNSUP when the fast path does not apply (caller falls back to the generic kernel)
+int Ad_star3_ring_f32(void* out, const void* phi, const void* m, int64_t N, const int64_t* sh, int rev,
+                      cudaStream_t s);  // adstar_ring.cu
+
 int Ad_star3_f32(void* out, const void* phi, const void* m, int64_t N, const int64_t* sh, int rev, cudaStream_t s) {
   if (!fast3_ok(out, phi, m, N, sh)) return LGM_EUNSUP;
+  {  // power-of-two rows: the stencil operand staged in shared memory (TMA ring)
+    const int rc = Ad_star3_ring_f32(out, phi, m, N, sh, rev, s);
+    if (rc != LGM_EUNSUP) return rc;
+  }
   constexpr int BX = LGM_GATHER_BX;
   dim3 grid((unsigned)cdiv(sh[2], 32 * LGM_GATHER_NV), (unsigned)cdiv(sh[1], (8 / BX) * LGM_GATHER_NR), (unsigned)(N * cdiv(sh[0], BX))), block(32, 8 / BX, BX);
   gather3_kernel<0, LGM_GATHER_NV, BX, LGM_GATHER_NR><<<grid, block, 0, s>>>((float*)out, (const float*)phi, (const float*)m, (int)sh[0],

@@ -216,3 +216,44 @@ def test_quarter_slab_path_matches_cluster_path(tmp_path):
             continue
         a, b = res["qslab"][k], res["cluster"][k]
         assert ((a - b).norm() / b.norm()).item() <= 1e-6, k
+
+
+_ARING_SCRIPT = """
+import sys, torch
+sys.path.insert(0, sys.argv[2])
+import lagomorph_b200 as lm
+from util import smooth_field
+outs = {}
+for i, (sh, amp) in enumerate((((2, 3, 20, 24, 128), 3.0), ((1, 3, 17, 13, 64), 5.0), ((2, 3, 9, 10, 32), 2.0),
+                               ((1, 3, 6, 11, 256), 4.0), ((1, 3, 36, 8, 128), 60.0))):
+    phi = smooth_field(sh, torch.float32, 40 + i, amp=amp, sigma=2.0)
+    phi[:, :, 0] -= 2.0       # border bands pushed out of range: clamped corners, clamped stencil rows
+    phi[..., -1] += 2.5
+    m = torch.randn(sh, generator=torch.Generator().manual_seed(50 + i))
+    outs["a%d" % i] = lm.Ad_star(phi.cuda(), m.cuda()).cpu()
+torch.save(outs, sys.argv[1])
+"""
+
+
+def test_ring_adstar_bit_identical_to_planar_kernel(tmp_path):
+    """Ad_star with the stencil operand staged in a shared-memory ring (csrc/adstar_ring.cu) == the planar
+    L1 kernel (LGM_NO_ADSTAR_RING=1, read once per process: two subprocesses), bit for bit: partial y
+    tiles, x extents that are not a multiple of the march length, Z = 32 ... 256, borders."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "aring.py"
+    script.write_text("import sys\nsys.path.insert(0, %r)\n" % os.path.join(root, "tests") + _ARING_SCRIPT)
+    res = {}
+    for tag, env in (("ring", {"LGM_ADSTAR_RING_256": "1"}), ("planar", {"LGM_NO_ADSTAR_RING": "1"})):
+        out = str(tmp_path / (tag + ".pt"))
+        e = dict(os.environ)
+        e.pop("LGM_NO_ADSTAR_RING", None)
+        e.update(env)
+        subprocess.check_call([sys.executable, str(script), out, root], env=e)
+        res[tag] = torch.load(out)
+    assert res["ring"].keys() == res["planar"].keys() and len(res["ring"]) == 5
+    for k in res["ring"]:
+        assert torch.isfinite(res["ring"][k]).all()
+        assert torch.equal(res["ring"][k], res["planar"][k]), k
