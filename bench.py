@@ -334,7 +334,7 @@ def bench_c5_deep(torch, lm, dev, hbm, metric, barrier, reduce_max, K=3, W=1, n=
     del net
     torch.cuda.empty_cache()
     return {"value": vs, "unit": "voxel-steps/s fwd+bwd (CNN time excluded)", "ms_total": ms, "ms_cnn_fwd_bwd": cnn_ms,
-            "hbm_roofline_frac_324B": vs * FWD_BWD_BYTES_PER_VOXEL_STEP / 1e9 / hbm,
+            "hbm_roofline_frac_324B": vs * (shoot_fwd_bwd_bytes_per_voxel(steps) / steps) / 1e9 / hbm,
             "config": {"shape": [n, n, n], "batch": batch, "epdiff_steps": steps, "cnn": "3 x Conv3d(3^3), 16 ch (cuDNN)"}}
 
 

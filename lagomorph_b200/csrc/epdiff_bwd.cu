@@ -134,14 +134,35 @@ compose_bwd3_kernel(float* __restrict__ dv, float* __restrict__ S, const float* 
   const int row = i * sx + j * sy;
   const float fi = (float)i, fj = (float)j;
   const int lane = threadIdx.x;
+  // Software pipeline over the chunks: the centre loads of chunk c4+1 are issued BEFORE chunk c4 is
+  // processed (the REDs are asm volatile with a memory clobber, so the compiler never moves a load
+  // across them itself): per chunk one dependent memory round trip (the corner gather) instead of two.
+  float nA[3], nG[3];
+  {
+    const int c0 = row + blockIdx.x * NV * 32 + lane;
+    if ((int)(blockIdx.x * NV * 32) < Z) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        nA[c] = __ldg(vn + c0 + (size_t)c * V);
+        nG[c] = __ldg(gn + c0 + (size_t)c * V);
+      }
+    }
+  }
 #pragma unroll 1
   for (int c4 = 0; c4 < NV; ++c4) {
     const int kb = (blockIdx.x * NV + c4) * 32;
     if (kb >= Z) break;  // Z % 32 == 0: chunks are whole
     const int k = kb + lane;
     const int c0 = row + k;
-    const float A0 = __ldg(vn + c0), A1 = __ldg(vn + c0 + V), A2 = __ldg(vn + c0 + 2 * V);
-    const float g0 = __ldg(gn + c0), g1 = __ldg(gn + c0 + V), g2 = __ldg(gn + c0 + 2 * V);
+    const float A0 = nA[0], A1 = nA[1], A2 = nA[2];
+    const float g0 = nG[0], g1 = nG[1], g2 = nG[2];
+    if (c4 + 1 < NV && kb + 32 < Z) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        nA[c] = __ldg(vn + c0 + 32 + (size_t)c * V);
+        nG[c] = __ldg(gn + c0 + 32 + (size_t)c * V);
+      }
+    }
     Corners cs;
     corner_setup<NEED_PHI>(cs, coord_f32(fi, A0, dh, dl), coord_f32(fj, A1, dh, dl),
                            coord_f32((float)k, A2, dh, dl), X, Y, Z, sx, sy, lane);
@@ -191,6 +212,16 @@ adstar_bwd3_kernel(float* __restrict__ mi_out, float* __restrict__ d_m0, float* 
   const int xm = (i > 0) ? -sx : 0, xp = (i < X - 1) ? sx : 0;
   const int ym = (j > 0) ? -sy : 0, yp = (j < Y - 1) ? sy : 0;
   const int lane = threadIdx.x;
+  // software pipeline over the chunks (see compose_bwd3_kernel): the displacement of chunk c4+1 is
+  // loaded before chunk c4 is processed, so a chunk's corner gather does not wait for a second round trip
+  float nA[3];
+  {
+    const int c0 = row + blockIdx.x * NV * 32 + lane;
+    if ((int)(blockIdx.x * NV * 32) < Z) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) nA[c] = __ldg(pn + c0 + (size_t)c * V);
+    }
+  }
 #pragma unroll 1
   for (int c4 = 0; c4 < NV; ++c4) {
     const int kb = (blockIdx.x * NV + c4) * 32;
@@ -199,7 +230,19 @@ adstar_bwd3_kernel(float* __restrict__ mi_out, float* __restrict__ d_m0, float* 
     const int c0 = row + k;
     const int zm = (k > 0) ? -1 : 0, zp = (k < Z - 1) ? 1 : 0;
     const float* pc = pn + c0;
-    const float A0 = __ldg(pc), A1 = __ldg(pc + V), A2 = __ldg(pc + 2 * V);
+    const float A0 = nA[0], A1 = nA[1], A2 = nA[2];
+    if (c4 + 1 < NV && kb + 32 < Z) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) nA[c] = __ldg(pc + 32 + (size_t)c * V);
+    }
+    // S was completed by compose_bwd3 (previous launch): its three values of this voxel are read with
+    // the other loads of the chunk, not in a round trip of their own after the splats
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (NEED_PHI) {
+      s0 = Sn[c0];
+      s1 = Sn[c0 + V];
+      s2 = Sn[c0 + 2 * V];
+    }
     // q_d = sum_c (D_d phi_c + delta_cd) dm_c   (jtvf backward d_w, cuda/diff.cu:417-431)
     float q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
@@ -234,9 +277,9 @@ adstar_bwd3_kernel(float* __restrict__ mi_out, float* __restrict__ d_m0, float* 
       if (NEED_M0) corner_splat(db[c], cs, q[c]);
     }
     if (NEED_PHI) {  // this thread owns voxel c0 of S now (the splats into S finished in compose_bwd3)
-      Sn[c0] += a0;
-      Sn[c0 + V] += a1;
-      Sn[c0 + 2 * V] += a2;
+      Sn[c0] = s0 + a0;
+      Sn[c0 + V] = s1 + a1;
+      Sn[c0 + 2 * V] = s2 + a2;
     }
   }
 }

@@ -17,7 +17,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 STALLS = [h for h in hdr if "issue_stalled" in h and h.endswith("_per_issue_active.ratio")]
-NAMES = {"gather3_kernel<0": "Ad_star", "gather3_kernel<(int)0": "Ad_star", "gather3_kernel<1": "compose",
+NAMES = {"adstar_ring_kernel": "Ad_star", "gather3_kernel<0": "Ad_star", "gather3_kernel<(int)0": "Ad_star", "gather3_kernel<1": "compose",
          "gather3_kernel<(int)1": "compose", "compose_ring_kernel": "compose", "slab_fwd": "slab_fwd", "slab_inv": "slab_inv", "xpass": "xpass"}
 traffic = {}
 with open(out_txt, "w") as f:

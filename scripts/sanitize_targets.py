@@ -1,7 +1,9 @@
 """Small invocations of every kernel family, for compute-sanitizer (memcheck / racecheck / synccheck):
   compute-sanitizer --tool racecheck python scripts/sanitize_targets.py
-The 256 x 256 slabs go through the 4-CTA cluster kernels (DSMEM all-to-all, csrc/fluid.cu)."""
+The 256 x 256 slabs go through the 4-CTA cluster kernels (DSMEM all-to-all, csrc/fluid.cu) for beta != 0 or
+X < 64, through the quarter-slab kernels (csrc/qslab.cuh) otherwise."""
 import os, sys
+os.environ["LGM_ADSTAR_RING_256"] = "1"   # also the (slower, off by default) 256-row instance of the Ad_star ring
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import lagomorph_b200 as lm
@@ -17,6 +19,15 @@ for params in ([0.1, 0.0, 0.01], [0.1, 0.02, 0.01]):
         back = met.flat(v)
         print("fluid", params, sh, float((back - m).abs().max()))
 met = lm.FluidMetric([0.1, 0.0, 0.01])
+mq = torch.randn((1, 3, 64, 256, 256), device=dev)     # quarter-slab kernels + their X pass
+print("qslab", float((met.flat(met.sharp(mq)) - mq).abs().max()))
+print("qslab shoot", float(lm.expmap(met, mq * (2.0 / met.sharp(mq).abs().max()), num_steps=2).abs().max()))
+del mq
+# Ad_star through the shared-memory ring (stencil operand staged by bulk async copies), every row length
+for shp in [(6, 10, 32), (9, 12, 64), (20, 20, 128), (5, 9, 256)]:
+    phi = (torch.rand((2, 3) + shp, device=dev) - 0.5) * 6.0
+    mm = torch.randn((2, 3) + shp, device=dev)
+    print("adstar ring", shp, float(lm.Ad_star(phi, mm).abs().max()))
 sh = (16, 24, 32)
 m0 = torch.randn((2, 3) + sh, device=dev)
 m0 = m0 * (3.0 / met.sharp(m0).abs().max())
