@@ -36,7 +36,7 @@ constexpr int kARing = 4;
 template <int NV, int WPR>
 __global__ void __launch_bounds__(256, LGM_ARING_MINB)
 adstar_ring_kernel(float* __restrict__ out, const float* __restrict__ phi, const float* __restrict__ m, int X, int Y,
-                   int rev) {
+                   int xs, int rev) {
   constexpr int TY = 8 / WPR, ROWS = TY + 2, Z = 32 * NV * WPR;
   extern __shared__ __align__(128) unsigned char aring_raw[];
   float* ring = reinterpret_cast<float*>(aring_raw);                 // [kARing][3][ROWS][Z]
@@ -48,7 +48,7 @@ adstar_ring_kernel(float* __restrict__ out, const float* __restrict__ phi, const
   const int y0t = byi * TY, yb = y0t - 1;
   const int j = y0t + w / WPR;
   const int zoff = (w % WPR) * (32 * NV);
-  const int xs0 = bxi * LGM_ARING_XS, xs1 = min(X, xs0 + LGM_ARING_XS);  // slabs [xs0, xs1)
+  const int xs0 = bxi * xs, xs1 = min(X, xs0 + xs);  // slabs [xs0, xs1)
   const int sy = Z, sx = Y * Z;
   const int V = X * sx;
   const int ylo = max(yb, 0), yhi = min(y0t + TY, Y - 1);             // staged rows of every plane
@@ -162,14 +162,19 @@ int Ad_star3_ring_f32(void* out, const void* phi, const void* m, int64_t N, cons
   if (((uintptr_t)phi & 15) != 0) return LGM_EUNSUP;  // bulk copies need 16-byte aligned rows
   const int wpr = Z == 256 ? 2 : 1, TY = 8 / wpr;
   const size_t smem = (size_t)kARing * 3 * (TY + 2) * Z * 4 + kARing * 8;
-  dim3 grid((unsigned)cdiv(X, LGM_ARING_XS), (unsigned)cdiv(Y, TY), (unsigned)N), block(32, 8);
+  // x slabs marched by one CTA: LGM_ARING_XS for large batches (each plane row is fetched (TY+2)/TY * (xs+2)/xs times);
+  // shorter marches when the grid would not fill the GPU twice over (small batches: chunks of expmap_host,
+  // single registrations), so that CTAs = N * Y/TY * X/xs stays above ~6 per SM
+  int xs = LGM_ARING_XS;
+  while (xs > 4 && N * cdiv(Y, TY) * cdiv(X, xs) < 6 * 148) xs /= 2;
+  dim3 grid((unsigned)cdiv(X, xs), (unsigned)cdiv(Y, TY), (unsigned)N), block(32, 8);
 #define LGM_ARING(NV_, WPR_)                                                                                        \
   do {                                                                                                              \
     cudaError_t e = cudaFuncSetAttribute(adstar_ring_kernel<NV_, WPR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem);                                                                \
     if (e != cudaSuccess) return set_error((int)e, "Ad_star ring smem: %s", cudaGetErrorString(e));                 \
     adstar_ring_kernel<NV_, WPR_><<<grid, block, smem, s>>>((float*)out, (const float*)phi, (const float*)m, (int)X, \
-                                                            (int)Y, rev);                                           \
+                                                            (int)Y, xs, rev);                                           \
   } while (0)
   if (Z == 32) LGM_ARING(1, 1);
   else if (Z == 64) LGM_ARING(2, 1);

@@ -40,7 +40,7 @@ constexpr unsigned kFullMask = 0xffffffffu;
 template <int NV, int WPR>
 __global__ void __launch_bounds__(256, LGM_RING_MINB)
 compose_ring_kernel(float* __restrict__ out, const float* __restrict__ u, const float* __restrict__ v, int X, int Y,
-                    float dh, float dl, float dsr, float dtr, int rev) {
+                    float dh, float dl, float dsr, float dtr, int xs, int rev) {
   constexpr int TY = 8 / WPR, ROWS = TY + 2, Z = 32 * NV * WPR;
   extern __shared__ __align__(128) unsigned char ring_raw[];
   float* ring = reinterpret_cast<float*>(ring_raw);                 // [kRing][3][ROWS][Z]
@@ -52,7 +52,7 @@ compose_ring_kernel(float* __restrict__ out, const float* __restrict__ u, const 
   const int y0t = byi * TY, yb = y0t - 1;
   const int j = y0t + w / WPR;
   const int zoff = (w % WPR) * (32 * NV);
-  const int xs0 = bxi * LGM_RING_XS, xs1 = min(X, xs0 + LGM_RING_XS);  // slabs [xs0, xs1)
+  const int xs0 = bxi * xs, xs1 = min(X, xs0 + xs);  // slabs [xs0, xs1)
   const int sy = Z, sx = Y * Z;
   const int V = X * sx;
   const int ylo = max(yb, 0), yhi = min(y0t + TY, Y - 1);             // staged rows of every plane
@@ -184,14 +184,19 @@ int compose3_ring_f32(void* out, const void* u, const void* v, int64_t N, const 
   const float dh = (float)ds, dl = (float)(ds - (double)dh);
   const int wpr = Z == 256 ? 2 : 1, TY = 8 / wpr;
   const size_t smem = (size_t)kRing * 3 * (TY + 2) * Z * 4 + kRing * 8;
-  dim3 grid((unsigned)cdiv(X, LGM_RING_XS), (unsigned)cdiv(Y, TY), (unsigned)N), block(32, 8);
+  // x slabs marched by one CTA: LGM_RING_XS for large batches (each plane row is fetched (TY+2)/TY * (xs+2)/xs times);
+  // shorter marches when the grid would not fill the GPU twice over (small batches: chunks of expmap_host,
+  // single registrations), so that CTAs = N * Y/TY * X/xs stays above ~6 per SM
+  int xs = LGM_RING_XS;
+  while (xs > 4 && N * cdiv(Y, TY) * cdiv(X, xs) < 6 * 148) xs /= 2;
+  dim3 grid((unsigned)cdiv(X, xs), (unsigned)cdiv(Y, TY), (unsigned)N), block(32, 8);
 #define LGM_RING(NV_, WPR_)                                                                                          \
   do {                                                                                                               \
     cudaError_t e = cudaFuncSetAttribute(compose_ring_kernel<NV_, WPR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem);                                                                 \
     if (e != cudaSuccess) return set_error((int)e, "compose ring smem: %s", cudaGetErrorString(e));                  \
     compose_ring_kernel<NV_, WPR_><<<grid, block, smem, s>>>((float*)out, (const float*)u, (const float*)v, (int)X,   \
-                                                             (int)Y, dh, dl, (float)ds, (float)dt, rev);             \
+                                                             (int)Y, dh, dl, (float)ds, (float)dt, xs, rev);             \
   } while (0)
   if (Z == 32) LGM_RING(1, 1);
   else if (Z == 64) LGM_RING(2, 1);

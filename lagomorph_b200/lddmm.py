@@ -316,6 +316,57 @@ def _auto_chunks(N, num_steps=10, cap=5, ratio=None):
     return sizes
 
 
+def _ramp_chunks(N):
+    """1, 2, 3, ... up and down again: [1, 2, 3, 4, 3, 2, 1] for N = 16. Small chunks at both ends (their
+    copies are exposed), every copy hidden behind a neighbour's shoot as long as a subject's copy is
+    shorter than its shoot; the remainder that does not fit the triangle widens the middle."""
+    k = 1
+    while (k + 1) * (k + 1) <= N:
+        k += 1
+    sizes = list(range(1, k + 1)) + list(range(k - 1, 0, -1))   # sums to k*k
+    left = N - k * k
+    mid = len(sizes) // 2
+    order = sorted(range(len(sizes)), key=lambda i: (abs(i - mid), i))   # the rest widens the middle first
+    for t in range(left):
+        sizes[order[t % len(order)]] += 1
+    return [c for c in sizes if c > 0]
+
+
+_BEST_CHUNKS = {}   # (device, subject shape, dtype, steps, N) -> chunk schedule measured best on this box
+
+
+def _measured_chunks(metric, m0_host, T, num_steps, out, dev):
+    """chunk="auto": the schedule from the copy/compute model (_auto_chunks) and the ramp (_ramp_chunks)
+    are each run once on the real data the first time a (device, shape, steps, batch) combination is seen;
+    the faster one is kept. (The model assumes a shoot's time is proportional to its batch; small chunks
+    are slower than that, and by how much depends on the GPU.)"""
+    N = m0_host.shape[0]
+    key = (dev.index, tuple(m0_host.shape[1:]), m0_host.dtype, int(num_steps), N)
+    if key in _BEST_CHUNKS:
+        return _BEST_CHUNKS[key]
+    model = _auto_chunks(N, num_steps, ratio=_copy_compute_ratio(metric, m0_host, T, num_steps, dev))
+    cands = [model]
+    ramp = _ramp_chunks(N)
+    if ramp != model and N >= 4:
+        cands.append(ramp)
+    if len(cands) == 1 or torch.cuda.is_current_stream_capturing():
+        return model
+    best, best_ms = model, None
+    for sizes in cands:
+        expmap_host(metric, m0_host, T=T, num_steps=num_steps, out=out, device=dev, chunk=sizes)   # plan, warm-up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        expmap_host(metric, m0_host, T=T, num_steps=num_steps, out=out, device=dev, chunk=sizes)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if best_ms is None or ms < best_ms:
+            best, best_ms = sizes, ms
+    _BEST_CHUNKS[key] = best
+    return best
+
+
 def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chunk="auto", graphs=True):
     """Shoot momenta that live in (pinned) HOST memory and return the deformations in host memory.
 
@@ -336,7 +387,7 @@ def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chu
         return out
     # chunk: "auto", an int (uniform chunks) or a list of chunk sizes.
     if isinstance(chunk, str):
-        sizes = _auto_chunks(N, num_steps, ratio=_copy_compute_ratio(metric, m0_host, T, num_steps, dev))
+        sizes = _measured_chunks(metric, m0_host, T, num_steps, out, dev)
     elif isinstance(chunk, (list, tuple)):
         sizes = [int(c) for c in chunk if int(c) > 0]
         assert sum(sizes) == N, "chunk sizes must add up to the batch"

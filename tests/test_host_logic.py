@@ -96,6 +96,12 @@ def test_expmap_host_chunk_schedule(lm):
         for N in (1, 2, 7, 16, 64):
             c = _auto_chunks(N, 10, ratio=r)
             assert sum(c) == N and min(c) >= 1 and max(c) <= 6  # cap 5, +1 when a stray single is merged
+    # the second candidate expmap_host times against it: 1, 2, 3, ... up and down again
+    from lagomorph_b200.lddmm import _ramp_chunks
+    assert _ramp_chunks(16) == [1, 2, 3, 4, 3, 2, 1] and _ramp_chunks(9) == [1, 2, 3, 2, 1]
+    for N in range(1, 80):
+        c = _ramp_chunks(N)
+        assert sum(c) == N and min(c) >= 1 and c == sorted(c[:len(c) // 2 + 1]) + sorted(c[len(c) // 2 + 1:], reverse=True), (N, c)
     with pytest.raises(RuntimeError, match="host tensors"):
         lm.expmap_host(lm.FluidMetric(), torch.zeros(1, 3, 4, 4, 4, device="meta") if False else _FakeCuda())
 
