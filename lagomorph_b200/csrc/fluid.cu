@@ -809,11 +809,20 @@ __device__ __forceinline__ R oo_sqrt_fast(R x) {
 // arithmetic sqrt(fl(x*x)) == |x| exactly (no over-/underflow: Lm <= 1e-8f is the safe_sqrt branch --
 // for a float x, (double)x < 1e-8 <=> x <= 1e-8f -- and an infinite Lm keeps sqrt's infinity), so the
 // result is bit-identical to oo_sqrt_fast(Lm) at a third of its instructions (no MUFU.RSQ + fix-up).
+// The reciprocal itself: MUFU.RCP + one FMA Newton step, which IS the round-to-nearest reciprocal for every
+// float in [2^-64, 2^64] (scripts/micro/rcp_rn.cu checks all 1.07e9 of them against __frcp_rn on the GPU:
+// 0 mismatches) without __frcp_rn's range-check branch and slow-path call around every element; arguments
+// outside that range (alpha or gamma beyond 1e19) take __frcp_rn.
+__device__ __noinline__ float rcp_rn_slow(float s) { return __frcp_rn(s); }  // out of line: cold path
 template <typename R>
 __device__ __forceinline__ R oo_lambda_fast(R lambda, R Lm) {
   if constexpr (sizeof(R) == 4) {
     const float s = (Lm <= 1e-8f) ? 1e-4f : (Lm == INFINITY ? Lm : fabsf(lambda));
-    return (R)__frcp_rn(s);
+    if (__builtin_expect(!(s <= 18446744073709551616.f), 0)) return (R)rcp_rn_slow(s);   // > 2^64, inf, NaN
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    const float e = __fmaf_rn(-s, r, 1.f);
+    return (R)__fmaf_rn(r, e, r);
   } else {
     return oo_sqrt<R>(Lm);
   }
