@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: scripts/r3_variants.sh <workload> <variant names...>; times the default build and every variant (one gpurun call)
+# usage: scripts/variants.sh <workload> <variant names...>; times the default build and every variant (one gpurun call)
 wl=$1; shift
 mkdir -p gpurun_out
 python scripts/variant_bench.py $wl 2>&1 | tail -1
