@@ -207,10 +207,15 @@ def nccl_log_summary():
     """what NCCL's own INIT log of this process says about the communicator (file set in main())"""
     import glob
     import re
-    pat = os.environ.get("NCCL_DEBUG_FILE", "").replace("%p", str(os.getpid()))
+    raw = os.environ.get("NCCL_DEBUG_FILE", "")
+    pat = raw.replace("%p", str(os.getpid())).replace("%h", "*")
     out = {"log": pat or None}
     try:
-        txt = "".join(open(f, errors="replace").read() for f in glob.glob(pat)) if pat else ""
+        files = glob.glob(pat) if pat else []
+        if not files and raw:   # NCCL may expand %p / %h differently: any rank's log of this launch will do
+            files = sorted(glob.glob(raw.replace("%p", "*").replace("%h", "*")))[:1]
+        out["log_bytes"] = sum(os.path.getsize(f) for f in files)
+        txt = "".join(open(f, errors="replace").read() for f in files)
         m = re.search(r"NCCL version ([0-9.+a-z]+)", txt)
         out["version"] = m.group(1) if m else None
         m = re.search(r"nranks (\d+)", txt)
@@ -426,6 +431,13 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # NCCL's communicator log goes to a file (stdout must stay ONE JSON line); rank 0 summarises it in
+        # also.c3_atlas.nccl. Set BEFORE torch is imported: NCCL latches its debug settings on first use.
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"   # (the image presets NCCL_DEBUG=VERSION)
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/lgm_nccl_%d.%%p.log" % os.getppid())
     import torch
     import torch.distributed as dist
     import lagomorph_b200 as lm
@@ -438,11 +450,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     numa, numa_why = bind_to_gpu_numa_node(local_rank) if world > 1 else (None, "single rank: not bound")
     if world > 1:
-        # NCCL's communicator log goes to a file (stdout must stay ONE JSON line); rank 0 summarises it
-        # in also.c3_atlas.nccl
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/lgm_nccl_%d.%%p.log" % os.getppid())
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1
 
