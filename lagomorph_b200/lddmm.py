@@ -332,49 +332,63 @@ def _ramp_chunks(N):
     return [c for c in sizes if c > 0]
 
 
-_BEST_CHUNKS = {}   # (device, subject shape, dtype, steps, N) -> chunk schedule measured best on this box
+_BEST_CHUNKS = {}   # (device, subject shape, dtype, steps, N, streams) -> (chunk schedule, compute streams) measured best
 
 
-def _measured_chunks(metric, m0_host, T, num_steps, out, dev):
-    """chunk="auto": the schedule from the copy/compute model (_auto_chunks) and the ramp (_ramp_chunks)
-    are each run once on the real data the first time a (device, shape, steps, batch) combination is seen;
-    the faster one is kept. (The model assumes a shoot's time is proportional to its batch; small chunks
-    are slower than that, and by how much depends on the GPU.)"""
+def _measured_chunks(metric, m0_host, T, num_steps, out, dev, streams=None):
+    """chunk="auto": candidate (schedule, compute streams) pairs are each run once on the real data the first
+    time a (device, shape, steps, batch) combination is seen, and the fastest is kept: the schedule from the
+    copy/compute model (_auto_chunks) and the ramp (_ramp_chunks) on one compute stream, and -- when the
+    caller leaves `streams` open -- the ramp, pairs and single subjects on two. (The model assumes a shoot's
+    time is proportional to its batch; small chunks are slower than that on ONE stream because none of their
+    ~50 launches fills the GPU, but two of them in flight do: C2 on a B200, r3_e2e_streams.log:
+    ramp x 1 stream 14.07 ms, single subjects x 1 stream 16.1 ms, single subjects x 2 streams 12.6 ms.)"""
     N = m0_host.shape[0]
-    key = (dev.index, tuple(m0_host.shape[1:]), m0_host.dtype, int(num_steps), N)
+    key = (dev.index, tuple(m0_host.shape[1:]), m0_host.dtype, int(num_steps), N, streams)
     if key in _BEST_CHUNKS:
         return _BEST_CHUNKS[key]
+    one = 1 if streams is None else max(1, int(streams))
     model = _auto_chunks(N, num_steps, ratio=_copy_compute_ratio(metric, m0_host, T, num_steps, dev))
-    cands = [model]
+    cands = [(model, one)]
     ramp = _ramp_chunks(N)
     if ramp != model and N >= 4:
-        cands.append(ramp)
+        cands.append((ramp, one))
+    if N >= 4 and (streams is None or one > 1):
+        two = 2 if streams is None else one
+        pairs = [1, 1] + [2] * ((N - 4) // 2) + [1] * ((N - 4) % 2) + [1, 1]
+        for sizes in (ramp, pairs, [1] * N):
+            if (sizes, two) not in cands:
+                cands.append((sizes, two))
     if len(cands) == 1 or torch.cuda.is_current_stream_capturing():
-        return model
-    best, best_ms = model, None
-    for sizes in cands:
-        expmap_host(metric, m0_host, T=T, num_steps=num_steps, out=out, device=dev, chunk=sizes)   # plan, warm-up
+        return cands[0]
+    best, best_ms = cands[0], None
+    for sizes, ns in cands:
+        expmap_host(metric, m0_host, T=T, num_steps=num_steps, out=out, device=dev, chunk=sizes, streams=ns)   # plan, warm-up
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
         e0.record()
-        expmap_host(metric, m0_host, T=T, num_steps=num_steps, out=out, device=dev, chunk=sizes)
+        expmap_host(metric, m0_host, T=T, num_steps=num_steps, out=out, device=dev, chunk=sizes, streams=ns)
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)
         if best_ms is None or ms < best_ms:
-            best, best_ms = sizes, ms
+            best, best_ms = (sizes, ns), ms
+    for k in [k for k in _HOST_PLANS if k[-2] != tuple(best[0]) or k[-1] != best[1] + 2]:
+        _HOST_PLANS.pop(k)            # the losing candidates' graphs and buffers
     _BEST_CHUNKS[key] = best
     return best
 
 
-def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chunk="auto", graphs=True):
+def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chunk="auto", graphs=True, streams=None):
     """Shoot momenta that live in (pinned) HOST memory and return the deformations in host memory.
 
     Subjects are independent, so the batch is cut into chunks that flow through a three-stage
     pipeline on separate CUDA streams: host->device copy of chunk i+1, EPDiff shoot of chunk i,
-    device->host copy of chunk i-1 all overlap (PCIe is full duplex). (Shooting consecutive chunks
-    on alternating compute streams was measured: no gain, and erratic with the caching allocator.)
-    With graphs=True (default) every chunk's shoot is replayed as a cached CUDA graph (_host_plan).
+    device->host copy of chunk i-1 all overlap (PCIe is full duplex). With graphs=True (default) every
+    chunk's shoot is replayed as a cached CUDA graph (_host_plan). streams = number of compute streams:
+    consecutive chunks' graphs alternate between them, so that two small shoots are in flight at once
+    (graphs only: each graph owns its scratch memory). chunk="auto" with streams=None measures a few
+    (schedule, streams) candidates on first use and keeps the fastest (_measured_chunks).
     Same result as `expmap(metric, m0_host.cuda(), ...).cpu()`. No autograd.
     """
     if m0_host.is_cuda:
@@ -387,7 +401,9 @@ def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chu
         return out
     # chunk: "auto", an int (uniform chunks) or a list of chunk sizes.
     if isinstance(chunk, str):
-        sizes = _measured_chunks(metric, m0_host, T, num_steps, out, dev)
+        sizes, auto_ns = _measured_chunks(metric, m0_host, T, num_steps, out, dev, streams)
+        if streams is None:
+            streams = auto_ns
     elif isinstance(chunk, (list, tuple)):
         sizes = [int(c) for c in chunk if int(c) > 0]
         assert sum(sizes) == N, "chunk sizes must add up to the batch"
@@ -414,12 +430,21 @@ def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chu
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     s_in.wait_stream(cur)
     s_out.wait_stream(cur)
-    nbuf = 3
+    # streams: how many chunk shoots may be in flight at once. A chunk of one to four subjects does not
+    # fill the GPU through the ramp and the tail of each of its ~50 launches; with two compute streams the
+    # neighbouring chunk's kernels fill those gaps. Only with graphs (each graph owns its scratch memory).
+    ns = (1 if streams is None else max(1, int(streams))) if graphs else 1
+    nbuf = ns + 2
     plan = _host_plan(metric, m0_host, T, num_steps, dev, sizes, nbuf) if graphs else None
     if plan is not None:
         dbuf = plan["dbuf"]
     else:
+        ns = 1
         dbuf = [torch.empty((maxc,) + tuple(m0_host.shape[1:]), dtype=m0_host.dtype, device=dev) for _ in range(nbuf)]
+    s_comp = [cur] if ns == 1 else [torch.cuda.Stream(dev) for _ in range(ns)]
+    for sc in s_comp:
+        if sc is not cur:
+            sc.wait_stream(cur)
     in_done = [torch.cuda.Event() for _ in range(nbuf)]
     comp_done = [None] * nbuf  # input buffer of slot b has been consumed
     starts = [sum(sizes[:i]) for i in range(len(sizes))]
@@ -433,27 +458,34 @@ def expmap_host(metric, m0_host, T=1.0, num_steps=10, out=None, device=None, chu
             dbuf[b][:n].copy_(m0_host[starts[ci]:starts[ci] + n], non_blocking=True)
             in_done[b].record(s_in)
 
-    issue_h2d(0)
+    depth = nbuf - 1          # copies issued ahead of the chunk being shot
+    for ci in range(min(depth, len(starts))):
+        issue_h2d(ci)
     for ci, st in enumerate(starts):
         b = ci % nbuf
         n = sizes[ci]
-        if ci + 1 < len(starts):
-            issue_h2d(ci + 1)
-        cur.wait_event(in_done[b])
-        if plan is not None:
-            plan["graphs"][ci].replay()      # the chunk's num_steps x 5 launches as one CUDA graph
-            h = plan["outs"][ci]
-        else:
-            with torch.no_grad():
-                h = expmap(metric, dbuf[b][:n], T=T, num_steps=num_steps)
-        ev = torch.cuda.Event()
-        ev.record(cur)
+        sc = s_comp[ci % ns]
+        with torch.cuda.stream(sc):
+            sc.wait_event(in_done[b])
+            if plan is not None:
+                plan["graphs"][ci].replay()      # the chunk's num_steps x 5 launches as one CUDA graph
+                h = plan["outs"][ci]
+            else:
+                with torch.no_grad():
+                    h = expmap(metric, dbuf[b][:n], T=T, num_steps=num_steps)
+            ev = torch.cuda.Event()
+            ev.record(sc)
         comp_done[b] = ev
+        if ci + depth < len(starts):
+            issue_h2d(ci + depth)     # its buffer was chunk ci - 1's: that shoot is already in its stream
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev)
             out[st:st + n].copy_(h, non_blocking=True)
             if plan is None:
                 h.record_stream(s_out)
+    for sc in s_comp:
+        if sc is not cur:
+            cur.wait_stream(sc)
     cur.wait_stream(s_out)
     cur.wait_stream(s_in)
     return out

@@ -322,6 +322,14 @@ def test_expmap_host_pipeline(lm, orc):
     assert torch.equal(out1, ref1)
     from lagomorph_b200 import lddmm
     assert len(lddmm._HOST_PLANS) >= 1, "expmap_host fell back to the eager path"
+    # two and three compute streams (consecutive chunks' graphs in flight at once), repeated calls on
+    # alternating data so that a chunk's graph is replayed while its predecessor's results are still in flight
+    for ns, chunk in ((2, [1, 1, 1, 1, 1]), (2, [1, 2, 2]), (3, 1), (2, "auto")):
+        for rep in range(3):
+            a, r = (m0, ref) if rep % 2 == 0 else (m1, ref1)
+            out = lm.expmap_host(gm, a, num_steps=3, chunk=chunk, streams=ns)
+            torch.cuda.synchronize()
+            assert torch.equal(out, r), (ns, chunk, rep)
 
 
 @pytest.mark.parametrize("dim,sh", [(2, (16, 16)), (3, (8, 16, 16))])
