@@ -211,25 +211,72 @@ class LDDMMAtlasBuilder:
         return self.I.detach(), self.ms
 
     # ---- checkpoints ---------------------------------------------------------------------
-    # The reference writes one HDF5 file per rank (lddmm.py:238-285; h5py is not in this image): the
-    # same fields -- atlas, momenta concatenated over the rank's batches with their batch_sizes, and
-    # the four loss lists -- go through torch.save instead. Rank r > 0 appends ".rank<r>" to the name.
+    # The reference writes one HDF5 file per rank (lddmm.py:238-285): datasets "atlas", "momenta" (the
+    # rank's batches concatenated, attribute "batch_sizes") and the four loss lists. With h5py importable
+    # and a name ending in .h5 / .hdf5 / .hdf, save() writes exactly that layout and load() reads it (also
+    # files written by the reference); otherwise (h5py is not in this image) the same fields go through
+    # torch.save. load() tells the two apart by the HDF5 signature. Rank r > 0 appends ".rank<r>".
+    _HDF5_MAGIC = b"\x89HDF\r\n\x1a\n"
+
     def _ckpt_name(self, filename):
         return filename if self.rank == 0 else "%s.rank%d" % (filename, self.rank)
 
-    def save(self, filename):
-        self.initialize()
-        torch.save({
+    def _fields(self):
+        return {
             "atlas": self.I.detach().cpu(),
             "momenta": torch.cat([m.detach().cpu() for m in self.ms]) if self.ms else None,
             "batch_sizes": [int(m.shape[0]) for m in self.ms],
             "epoch_losses": list(self.epoch_losses), "epoch_reg_terms": list(self.epoch_reg_terms),
             "iter_losses": list(self.iter_losses), "iter_reg_terms": list(self.iter_reg_terms),
-        }, self._ckpt_name(filename))
+        }
+
+    def save(self, filename):
+        self.initialize()
+        f = self._fields()
+        name = self._ckpt_name(filename)
+        if str(filename).lower().endswith((".h5", ".hdf5", ".hdf")):
+            try:
+                import h5py
+            except ImportError:
+                h5py = None
+            if h5py is not None:
+                import numpy as np
+                with h5py.File(name, "w") as h:          # lddmm.py:251-262
+                    h.create_dataset("atlas", data=f["atlas"].numpy())
+                    if f["momenta"] is not None:         # lddmm.py:238-249
+                        hms = h.create_dataset("momenta", shape=tuple(f["momenta"].shape), dtype=np.float32)
+                        i = 0
+                        for m in self.ms:                # batch by batch: no second host copy of all momenta
+                            hms[i:i + m.shape[0], ...] = m.detach().cpu().numpy()
+                            i += m.shape[0]
+                        hms.attrs["batch_sizes"] = f["batch_sizes"]
+                    for k in ("epoch_losses", "epoch_reg_terms", "iter_losses", "iter_reg_terms"):
+                        h.create_dataset(k, data=np.asarray(f[k], dtype=np.float64))
+                return
+        torch.save(f, name)
 
     def load(self, filename, load_image=True, load_momenta=True, load_losses=True):
-        """Restore state saved by save(); call before initialize() / run() (like lddmm.py:272-285)."""
-        f = torch.load(self._ckpt_name(filename), map_location="cpu")
+        """Restore state saved by save() or by the reference's own save(); call before initialize() /
+        run() (like lddmm.py:272-285)."""
+        name = self._ckpt_name(filename)
+        with open(name, "rb") as fh:
+            is_hdf5 = fh.read(8) == self._HDF5_MAGIC
+        if is_hdf5:
+            try:
+                import h5py
+            except ImportError as e:
+                raise RuntimeError("%s is an HDF5 checkpoint and h5py is not installed" % name) from e
+            import numpy as np
+            with h5py.File(name, "r") as h:
+                f = {"atlas": torch.as_tensor(np.asarray(h["atlas"])) if load_image else None, "momenta": None}
+                if load_momenta and "momenta" in h:      # lddmm.py:264-270
+                    f["batch_sizes"] = [int(x) for x in h["momenta"].attrs["batch_sizes"]]
+                    f["momenta"] = torch.as_tensor(np.asarray(h["momenta"][...]))
+                if load_losses:
+                    for k in ("epoch_losses", "epoch_reg_terms", "iter_losses", "iter_reg_terms"):
+                        f[k] = [float(x) for x in np.asarray(h[k])]
+        else:
+            f = torch.load(name, map_location="cpu")
         if load_image:
             self.I0 = f["atlas"]
         if load_momenta and f["momenta"] is not None:
