@@ -32,28 +32,36 @@ namespace {
 constexpr int kARing = 4;
 
 // WPR warps share one z row (Z = 128 * WPR for Z > 128), a CTA of 8 warps covers TY = 8 / WPR rows;
-// NV chunks of 32 per thread; blockDim = (32, 8). Z = 32 * NV * WPR is a compile-time constant.
-template <int NV, int WPR>
+// NV chunks of 32 per thread; blockDim = (32, 8). Z = 32 * NV * WPR * NZT is a compile-time constant.
+// NZT > 1: the row is cut into NZT z tiles (gridDim.y = y tiles * NZT), each staged with kZHalo words of
+// halo on the inner side(s) as one bulk copy per row (ZW = 32 NV WPR + 2 kZHalo words, 16-byte aligned
+// start) instead of one per plane: 8 + 2 rows per CTA at Z = 256 with the shared memory of the Z = 128 kernel.
+constexpr int kZHalo = 4;
+template <int NV, int WPR, int NZT>
 __global__ void __launch_bounds__(256, LGM_ARING_MINB)
 adstar_ring_kernel(float* __restrict__ out, const float* __restrict__ phi, const float* __restrict__ m, int X, int Y,
                    int xs, int rev) {
-  constexpr int TY = 8 / WPR, ROWS = TY + 2, Z = 32 * NV * WPR;
+  constexpr int TY = 8 / WPR, ROWS = TY + 2, ZT = 32 * NV * WPR, Z = ZT * NZT;
+  constexpr int ZW = (NZT == 1) ? Z : ZT + 2 * kZHalo;               // staged words per row
   extern __shared__ __align__(128) unsigned char aring_raw[];
-  float* ring = reinterpret_cast<float*>(aring_raw);                 // [kARing][3][ROWS][Z]
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)kARing * 3 * ROWS * Z);
+  float* ring = reinterpret_cast<float*>(aring_raw);                 // [kARing][3][ROWS][ZW]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)kARing * 3 * ROWS * ZW);
   const int lane = threadIdx.x, w = threadIdx.y, tid = w * 32 + lane;
   const unsigned bxi = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
-  const unsigned byi = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const unsigned byz = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const unsigned byi = byz / NZT, zt = byz % NZT;
   const int n = blockIdx.z;
   const int y0t = byi * TY, yb = y0t - 1;
   const int j = y0t + w / WPR;
-  const int zoff = (w % WPR) * (32 * NV);
+  const int zoff = zt * ZT + (w % WPR) * (32 * NV);
+  // first staged z of this tile: its halo, shifted inwards at the two ends of the row
+  const int zlo = (NZT == 1) ? 0 : min(max((int)zt * ZT - kZHalo, 0), Z - ZW);
   const int xs0 = bxi * xs, xs1 = min(X, xs0 + xs);  // slabs [xs0, xs1)
   const int sy = Z, sx = Y * Z;
   const int V = X * sx;
   const int ylo = max(yb, 0), yhi = min(y0t + TY, Y - 1);             // staged rows of every plane
-  const unsigned plane_bytes = (unsigned)((yhi - ylo + 1) * Z * 4);
-  constexpr int CH = ROWS * Z;                                         // channel stride inside a ring slot
+  const unsigned plane_bytes = (unsigned)((yhi - ylo + 1) * ZW * 4);
+  constexpr int CH = ROWS * ZW;                                        // channel stride inside a ring slot
   const float* pn = phi + (size_t)n * 3 * V;
   const float* bn = m + (size_t)n * 3 * V;
   const float* bn1 = bn + V;
@@ -70,16 +78,29 @@ adstar_ring_kernel(float* __restrict__ out, const float* __restrict__ phi, const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto issue = [&](int p) {  // one thread: plane p of the three channels -> ring slot p % kARing
+  // warp 0: plane p of the three channels -> ring slot p % kARing. NZT == 1: lane 0 issues one bulk copy per
+  // channel (the staged rows are contiguous); NZT > 1: one bulk copy per (channel, row), spread over the lanes.
+  auto issue = [&](int p) {
     if (p < plo || p > phi_) return;
     const int slot = p & (kARing - 1);
-    mbar_expect_tx(&full[slot], 3 * plane_bytes);
-    float* dst = ring + (size_t)slot * 3 * CH + (ylo - yb) * Z;
-    const float* src = pn + (size_t)p * sx + (size_t)ylo * Z;
+    if (lane == 0) mbar_expect_tx(&full[slot], 3 * plane_bytes);
+    float* dst = ring + (size_t)slot * 3 * CH + (ylo - yb) * ZW;
+    const float* src = pn + (size_t)p * sx + (size_t)ylo * Z + zlo;
+    if constexpr (NZT == 1) {
+      if (lane == 0) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) bulk_g2s(dst + c * CH, src + (size_t)c * V, plane_bytes, &full[slot]);
+        for (int c = 0; c < 3; ++c) bulk_g2s(dst + c * CH, src + (size_t)c * V, plane_bytes, &full[slot]);
+      }
+    } else {
+      __syncwarp();
+      const int nr = yhi - ylo + 1;
+      for (int i = lane; i < 3 * nr; i += 32) {
+        const int c = i / nr, r = i - c * nr;
+        bulk_g2s(dst + c * CH + r * ZW, src + (size_t)c * V + (size_t)r * Z, (unsigned)(ZW * 4), &full[slot]);
+      }
+    }
   };
-  if (tid == 0) {
+  if (w == 0) {
     issue(xs0 - 1);
     issue(xs0);
     issue(xs0 + 1);
@@ -89,16 +110,18 @@ adstar_ring_kernel(float* __restrict__ out, const float* __restrict__ phi, const
   const bool rowok = j < Y;
   const float fj = (float)j;
   // ring row offsets of this thread's y row and its clamped y neighbours (diff.h: clamped indices)
-  const int rj = (j - yb) * Z;
-  const int rjm = (j > 0) ? rj - Z : rj, rjp = (j < Y - 1) ? rj + Z : rj;
+  const int rj = (j - yb) * ZW - zlo;   // + global z = column of the staged row
+  const int rjm = (j > 0) ? rj - ZW : rj, rjp = (j < Y - 1) ? rj + ZW : rj;
 
   for (int x = xs0; x < xs1; ++x) {
     __syncthreads();  // slab x-1 is done everywhere: the slot of plane x-2 may be overwritten by plane x+2
-    if (tid == 0) issue(x + 2);  // look-ahead (planes up to xs0+1 were issued in the prologue)
+    if (w == 0) issue(x + 2);  // look-ahead (planes up to xs0+1 were issued in the prologue)
     if (LGM_ARING_PF > 0 && tid >= 32 && tid < 35 && x + LGM_ARING_PF < xs1 && y0t + TY <= Y) {
       // the undisplaced rows of m0 for slab x + LGM_ARING_PF (where most of its gather lands) -> L2
-      const float* src = bn + (size_t)(tid - 32) * V + (size_t)(x + LGM_ARING_PF) * sx + (size_t)y0t * Z;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((unsigned)(TY * Z * 4)) : "memory");
+      // (NZT z tiles share the TY rows: tile zt takes rows [zt, zt + 1) * TY / NZT)
+      const float* src = bn + (size_t)(tid - 32) * V + (size_t)(x + LGM_ARING_PF) * sx +
+                         (size_t)(y0t + (int)zt * (TY / NZT)) * Z;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((unsigned)(TY / NZT * Z * 4)) : "memory");
     }
     const int need = min(x + 1, phi_);
     while (waited < need) {
@@ -155,31 +178,38 @@ int Ad_star3_ring_f32(void* out, const void* phi, const void* m, int64_t N, cons
   static const bool off = getenv("LGM_NO_ADSTAR_RING") != nullptr;  // kernel experiments
   const int64_t X = sh[0], Y = sh[1], Z = sh[2];
   if (off || X < 4 || Y < 2 || N > 65535 || X * Y * Z >= (1LL << 31) / 4) return LGM_EUNSUP;
-  // Z = 256 (two warps per row, 4 rows + 2 halo rows per CTA) measured SLOWER than the planar kernel on
-  // B200 (1.67 vs 1.54 ms at 8 x 256^3; Z = 128: 0.368 vs 0.398 ms at 16 x 128^3): rows up to 128 only
-  static const bool z256 = getenv("LGM_ADSTAR_RING_256") != nullptr;
-  if (!(Z == 32 || Z == 64 || Z == 128 || (Z == 256 && z256))) return LGM_EUNSUP;
+  // Z = 256: two z tiles of 128 + 8 words, 8 + 2 rows per CTA (LGM_ADSTAR_RING_256=0: planar kernel instead;
+  // =2: two warps per row, 4 + 2 full rows per CTA, measured slower than the planar kernel: 1.35 vs 1.25 ms
+  // at 8 x 256^3). The z-tile kernel itself times like the planar one (1.26 vs 1.25 ms) but the shoot is
+  // 2-3 % faster with it (r3_aring256.log: 22.0-22.5 vs 22.8-22.9 ms), every other kernel of the step
+  // running a little faster beside it on a power-capped GPU.
+  static const int mode256 = getenv("LGM_ADSTAR_RING_256") ? atoi(getenv("LGM_ADSTAR_RING_256")) : 1;
+  if (!(Z == 32 || Z == 64 || Z == 128 || (Z == 256 && mode256 != 0))) return LGM_EUNSUP;
   if (((uintptr_t)phi & 15) != 0) return LGM_EUNSUP;  // bulk copies need 16-byte aligned rows
-  const int wpr = Z == 256 ? 2 : 1, TY = 8 / wpr;
-  const size_t smem = (size_t)kARing * 3 * (TY + 2) * Z * 4 + kARing * 8;
+  const bool wide256 = mode256 == 2;
+  const int wpr = (Z == 256 && wide256) ? 2 : 1, TY = 8 / wpr;
+  const int nzt = (Z == 256 && !wide256) ? 2 : 1;
+  const int zw = nzt == 1 ? (int)Z : (int)Z / nzt + 2 * kZHalo;
+  const size_t smem = (size_t)kARing * 3 * (TY + 2) * zw * 4 + kARing * 8;
   // x slabs marched by one CTA: LGM_ARING_XS for large batches (each plane row is fetched (TY+2)/TY * (xs+2)/xs times);
   // shorter marches when the grid would not fill the GPU twice over (small batches: chunks of expmap_host,
   // single registrations), so that CTAs = N * Y/TY * X/xs stays above ~6 per SM
   int xs = LGM_ARING_XS;
-  while (xs > 4 && N * cdiv(Y, TY) * cdiv(X, xs) < 6 * 148) xs /= 2;
-  dim3 grid((unsigned)cdiv(X, xs), (unsigned)cdiv(Y, TY), (unsigned)N), block(32, 8);
-#define LGM_ARING(NV_, WPR_)                                                                                        \
-  do {                                                                                                              \
-    cudaError_t e = cudaFuncSetAttribute(adstar_ring_kernel<NV_, WPR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)smem);                                                                \
-    if (e != cudaSuccess) return set_error((int)e, "Ad_star ring smem: %s", cudaGetErrorString(e));                 \
-    adstar_ring_kernel<NV_, WPR_><<<grid, block, smem, s>>>((float*)out, (const float*)phi, (const float*)m, (int)X, \
-                                                            (int)Y, xs, rev);                                           \
+  while (xs > 4 && N * cdiv(Y, TY) * nzt * cdiv(X, xs) < 6 * 148) xs /= 2;
+  dim3 grid((unsigned)cdiv(X, xs), (unsigned)(cdiv(Y, TY) * nzt), (unsigned)N), block(32, 8);
+#define LGM_ARING(NV_, WPR_, NZT_)                                                                                   \
+  do {                                                                                                               \
+    cudaError_t e = cudaFuncSetAttribute(adstar_ring_kernel<NV_, WPR_, NZT_>,                                        \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
+    if (e != cudaSuccess) return set_error((int)e, "Ad_star ring smem: %s", cudaGetErrorString(e));                  \
+    adstar_ring_kernel<NV_, WPR_, NZT_><<<grid, block, smem, s>>>((float*)out, (const float*)phi, (const float*)m,   \
+                                                                  (int)X, (int)Y, xs, rev);                          \
   } while (0)
-  if (Z == 32) LGM_ARING(1, 1);
-  else if (Z == 64) LGM_ARING(2, 1);
-  else if (Z == 128) LGM_ARING(4, 1);
-  else LGM_ARING(4, 2);
+  if (Z == 32) LGM_ARING(1, 1, 1);
+  else if (Z == 64) LGM_ARING(2, 1, 1);
+  else if (Z == 128) LGM_ARING(4, 1, 1);
+  else if (wide256) LGM_ARING(4, 2, 1);
+  else LGM_ARING(4, 1, 2);
 #undef LGM_ARING
   count_launch("Ad_star", s);
   return finish(s, "lgm_Ad_star_fwd(ring)");

@@ -225,7 +225,7 @@ import lagomorph_b200 as lm
 from util import smooth_field
 outs = {}
 for i, (sh, amp) in enumerate((((2, 3, 20, 24, 128), 3.0), ((1, 3, 17, 13, 64), 5.0), ((2, 3, 9, 10, 32), 2.0),
-                               ((1, 3, 6, 11, 256), 4.0), ((1, 3, 36, 8, 128), 60.0))):
+                               ((1, 3, 6, 11, 256), 4.0), ((1, 3, 36, 8, 128), 60.0), ((1, 3, 21, 19, 256), 6.0))):
     phi = smooth_field(sh, torch.float32, 40 + i, amp=amp, sigma=2.0)
     phi[:, :, 0] -= 2.0       # border bands pushed out of range: clamped corners, clamped stencil rows
     phi[..., -1] += 2.5
@@ -253,7 +253,7 @@ def test_ring_adstar_bit_identical_to_planar_kernel(tmp_path):
         e.update(env)
         subprocess.check_call([sys.executable, str(script), out, root], env=e)
         res[tag] = torch.load(out)
-    assert res["ring"].keys() == res["planar"].keys() and len(res["ring"]) == 5
+    assert res["ring"].keys() == res["planar"].keys() and len(res["ring"]) == 6
     for k in res["ring"]:
         assert torch.isfinite(res["ring"][k]).all()
         assert torch.equal(res["ring"][k], res["planar"][k]), k
