@@ -11,7 +11,12 @@
 // planes of phi (rows y-1 .. y+TY, 3 channels): while slab x is worked on from planes x-1, x, x+1,
 // plane x+2 streams in. The m0 gather (displacements of several voxels) stays the L1 gather of
 // gather3.cu. Arithmetic and evaluation order are those of gather3_kernel<0>: results are bit-identical.
+// Rows of 256 voxels: the row is cut into two z tiles of 128 + 8 words (template parameter NZT) so that a
+// CTA keeps 8 + 2 rows in 64 KB, and each plane's box (3 channels x 10 rows x 136 words, strided in global
+// memory) is staged by one TMA TENSOR copy through a tensor map of the phi field (TM = true;
+// cp.async.bulk.tensor.4d, UTMALDG in SASS; ring_common.cuh: make_field_tmap / tma_box4_g2s).
 #include <cstdlib>
+#include <cstring>
 #include "gather_common.cuh"
 #include "ring_common.cuh"
 
@@ -37,15 +42,20 @@ constexpr int kARing = 4;
 // halo on the inner side(s) as one bulk copy per row (ZW = 32 NV WPR + 2 kZHalo words, 16-byte aligned
 // start) instead of one per plane: 8 + 2 rows per CTA at Z = 256 with the shared memory of the Z = 128 kernel.
 constexpr int kZHalo = 4;
-template <int NV, int WPR, int NZT>
+template <int NV, int WPR, int NZT, bool TM>
 __global__ void __launch_bounds__(256, LGM_ARING_MINB)
 adstar_ring_kernel(float* __restrict__ out, const float* __restrict__ phi, const float* __restrict__ m, int X, int Y,
-                   int xs, int rev) {
+                   int xs, int rev, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
   constexpr int TY = 8 / WPR, ROWS = TY + 2, ZT = 32 * NV * WPR, Z = ZT * NZT;
   constexpr int ZW = (NZT == 1) ? Z : ZT + 2 * kZHalo;               // staged words per row
+  constexpr int CH = ROWS * ZW;                                      // channel stride inside a ring slot
+  constexpr int SLOT = TM ? (3 * CH + 31) / 32 * 32 : 3 * CH;        // slot stride: 128-byte aligned for TMA tensor copies
   extern __shared__ __align__(128) unsigned char aring_raw[];
   float* ring = reinterpret_cast<float*>(aring_raw);                 // [kARing][3][ROWS][ZW]
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)kARing * 3 * ROWS * ZW);
+  // mbarriers: behind the ring, or (z tiles) in the padding of slot 0 so that the CTA stays at 64 KB:
+  // three CTAs per SM inside the 196 KB carve-out (one KB more and the SM drops to two, or to a smaller L1)
+  static_assert(!TM || SLOT - 3 * CH >= 2 * kARing, "no room for the mbarriers in the slot padding");
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (TM ? (size_t)3 * CH : (size_t)kARing * SLOT));
   const int lane = threadIdx.x, w = threadIdx.y, tid = w * 32 + lane;
   const unsigned bxi = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const unsigned byz = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
@@ -61,7 +71,6 @@ adstar_ring_kernel(float* __restrict__ out, const float* __restrict__ phi, const
   const int V = X * sx;
   const int ylo = max(yb, 0), yhi = min(y0t + TY, Y - 1);             // staged rows of every plane
   const unsigned plane_bytes = (unsigned)((yhi - ylo + 1) * ZW * 4);
-  constexpr int CH = ROWS * ZW;                                        // channel stride inside a ring slot
   const float* pn = phi + (size_t)n * 3 * V;
   const float* bn = m + (size_t)n * 3 * V;
   const float* bn1 = bn + V;
@@ -83,8 +92,17 @@ adstar_ring_kernel(float* __restrict__ out, const float* __restrict__ phi, const
   auto issue = [&](int p) {
     if (p < plo || p > phi_) return;
     const int slot = p & (kARing - 1);
+    if constexpr (TM) {
+      // one tensor copy: box (3 channels, 1 plane, ROWS rows from yb, ZW words from zlo); rows outside the
+      // volume arrive as zeros and are never read (clamped stencil rows)
+      if (lane == 0) {
+        mbar_expect_tx(&full[slot], (unsigned)(3 * CH * 4));
+        tma_box4_g2s(ring + (size_t)slot * SLOT, &tmap, zlo, yb, p, 3 * n, &full[slot]);
+      }
+      return;
+    }
     if (lane == 0) mbar_expect_tx(&full[slot], 3 * plane_bytes);
-    float* dst = ring + (size_t)slot * 3 * CH + (ylo - yb) * ZW;
+    float* dst = ring + (size_t)slot * SLOT + (ylo - yb) * ZW;
     const float* src = pn + (size_t)p * sx + (size_t)ylo * Z + zlo;
     if constexpr (NZT == 1) {
       if (lane == 0) {
@@ -133,9 +151,9 @@ adstar_ring_kernel(float* __restrict__ out, const float* __restrict__ phi, const
     if (!rowok) continue;
     const float fi = (float)x;
     const int row0 = x * sx + j * sy;
-    const float* sc = ring + (x & (kARing - 1)) * 3 * CH;                               // plane x
-    const float* sm = (x > 0) ? ring + ((x - 1) & (kARing - 1)) * 3 * CH : sc;          // plane x-1 (clamped)
-    const float* sp = (x < X - 1) ? ring + ((x + 1) & (kARing - 1)) * 3 * CH : sc;      // plane x+1 (clamped)
+    const float* sc = ring + (x & (kARing - 1)) * SLOT;                               // plane x
+    const float* sm = (x > 0) ? ring + ((x - 1) & (kARing - 1)) * SLOT : sc;          // plane x-1 (clamped)
+    const float* sp = (x < X - 1) ? ring + ((x + 1) & (kARing - 1)) * SLOT : sc;      // plane x+1 (clamped)
 #pragma unroll
     for (int c4 = 0; c4 < NV; ++c4) {
       const int k = zoff + c4 * 32 + lane;
@@ -178,11 +196,12 @@ int Ad_star3_ring_f32(void* out, const void* phi, const void* m, int64_t N, cons
   static const bool off = getenv("LGM_NO_ADSTAR_RING") != nullptr;  // kernel experiments
   const int64_t X = sh[0], Y = sh[1], Z = sh[2];
   if (off || X < 4 || Y < 2 || N > 65535 || X * Y * Z >= (1LL << 31) / 4) return LGM_EUNSUP;
-  // Z = 256: two z tiles of 128 + 8 words, 8 + 2 rows per CTA (LGM_ADSTAR_RING_256=0: planar kernel instead;
-  // =2: two warps per row, 4 + 2 full rows per CTA, measured slower than the planar kernel: 1.35 vs 1.25 ms
-  // at 8 x 256^3). The z-tile kernel itself times like the planar one (1.26 vs 1.25 ms) but the shoot is
-  // 2-3 % faster with it (r3_aring256.log: 22.0-22.5 vs 22.8-22.9 ms), every other kernel of the step
-  // running a little faster beside it on a power-capped GPU.
+  // Z = 256: two z tiles of 128 + 8 words, 8 + 2 rows per CTA, each plane's box (3 channels x 10 rows x 136
+  // words) staged by ONE TMA tensor copy (cp.async.bulk.tensor.4d, UTMALDG). 8 x 256^3 on a B200
+  // (r3_aring256_tmap_ab3.log, r3_ring256_tmap_ab4.log): planar kernel 1.23-1.25 ms, z tiles with one bulk
+  // copy per row 1.22-1.27, with the tensor copy 1.09-1.14; shoot 22.86 -> 22.01 ms. LGM_ADSTAR_RING_256=0:
+  // planar kernel; =2: two warps per row, 4 + 2 full rows per CTA (round 2; slower than planar: 1.35).
+  // The same z tiles for compose measured SLOWER than its two-warps-per-row layout (0.97 vs 0.83 ms): not built in.
   static const int mode256 = getenv("LGM_ADSTAR_RING_256") ? atoi(getenv("LGM_ADSTAR_RING_256")) : 1;
   if (!(Z == 32 || Z == 64 || Z == 128 || (Z == 256 && mode256 != 0))) return LGM_EUNSUP;
   if (((uintptr_t)phi & 15) != 0) return LGM_EUNSUP;  // bulk copies need 16-byte aligned rows
@@ -190,26 +209,35 @@ int Ad_star3_ring_f32(void* out, const void* phi, const void* m, int64_t N, cons
   const int wpr = (Z == 256 && wide256) ? 2 : 1, TY = 8 / wpr;
   const int nzt = (Z == 256 && !wide256) ? 2 : 1;
   const int zw = nzt == 1 ? (int)Z : (int)Z / nzt + 2 * kZHalo;
-  const size_t smem = (size_t)kARing * 3 * (TY + 2) * zw * 4 + kARing * 8;
+
+  // z tiles: the staged box (3 channels x 10 rows x 136 words of one x plane) is one TMA tensor copy
+  // (LGM_ADSTAR_RING_TMAP=0: one bulk copy per row instead)
+  static const bool tmap_off = getenv("LGM_ADSTAR_RING_TMAP") != nullptr && atoi(getenv("LGM_ADSTAR_RING_TMAP")) == 0;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  const int use_tmap = (nzt > 1 && !tmap_off && make_field_tmap(&tmap, phi, N * 3, X, Y, Z, 3, TY + 2, zw)) ? 1 : 0;
+  const size_t slot_words = use_tmap ? ((size_t)3 * (TY + 2) * zw + 31) / 32 * 32 : (size_t)3 * (TY + 2) * zw;
+  const size_t smem = (size_t)kARing * slot_words * 4 + (use_tmap ? 0 : kARing * 8);
   // x slabs marched by one CTA: LGM_ARING_XS for large batches (each plane row is fetched (TY+2)/TY * (xs+2)/xs times);
   // shorter marches when the grid would not fill the GPU twice over (small batches: chunks of expmap_host,
   // single registrations), so that CTAs = N * Y/TY * X/xs stays above ~6 per SM
   int xs = LGM_ARING_XS;
   while (xs > 4 && N * cdiv(Y, TY) * nzt * cdiv(X, xs) < 6 * 148) xs /= 2;
   dim3 grid((unsigned)cdiv(X, xs), (unsigned)(cdiv(Y, TY) * nzt), (unsigned)N), block(32, 8);
-#define LGM_ARING(NV_, WPR_, NZT_)                                                                                   \
+#define LGM_ARING(NV_, WPR_, NZT_, TM_)                                                                                   \
   do {                                                                                                               \
-    cudaError_t e = cudaFuncSetAttribute(adstar_ring_kernel<NV_, WPR_, NZT_>,                                        \
+    cudaError_t e = cudaFuncSetAttribute(adstar_ring_kernel<NV_, WPR_, NZT_, TM_>,                                        \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
     if (e != cudaSuccess) return set_error((int)e, "Ad_star ring smem: %s", cudaGetErrorString(e));                  \
-    adstar_ring_kernel<NV_, WPR_, NZT_><<<grid, block, smem, s>>>((float*)out, (const float*)phi, (const float*)m,   \
-                                                                  (int)X, (int)Y, xs, rev);                          \
+    adstar_ring_kernel<NV_, WPR_, NZT_, TM_><<<grid, block, smem, s>>>((float*)out, (const float*)phi, (const float*)m,   \
+                                                                  (int)X, (int)Y, xs, rev, tmap, use_tmap);          \
   } while (0)
-  if (Z == 32) LGM_ARING(1, 1, 1);
-  else if (Z == 64) LGM_ARING(2, 1, 1);
-  else if (Z == 128) LGM_ARING(4, 1, 1);
-  else if (wide256) LGM_ARING(4, 2, 1);
-  else LGM_ARING(4, 1, 2);
+  if (Z == 32) LGM_ARING(1, 1, 1, false);
+  else if (Z == 64) LGM_ARING(2, 1, 1, false);
+  else if (Z == 128) LGM_ARING(4, 1, 1, false);
+  else if (wide256) LGM_ARING(4, 2, 1, false);
+  else if (use_tmap) LGM_ARING(4, 1, 2, true);
+  else LGM_ARING(4, 1, 2, false);
 #undef LGM_ARING
   count_launch("Ad_star", s);
   return finish(s, "lgm_Ad_star_fwd(ring)");

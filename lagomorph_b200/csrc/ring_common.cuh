@@ -1,6 +1,7 @@
 // ring_common.cuh -- mbarrier / bulk-copy (TMA engine) helpers of the kernels that stage x planes of a
 // field in a shared-memory ring (compose_ring.cu, adstar_ring.cu).
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 namespace lgm {
@@ -18,6 +19,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// one TMA tensor copy: the box of a rank-4 tensor map at coordinates (c0 fastest) -> shared memory
+// (UTMALDG in SASS); out-of-bounds elements of the box arrive as zeros and count towards the bytes
+__device__ __forceinline__ void tma_box4_g2s(void* dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3,
+                                             unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   unsigned ok;
   do {
@@ -26,6 +37,33 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                  : "r"(smem_u32(bar)), "r"(parity)
                  : "memory");
   } while (!ok);
+}
+
+// Host: tensor map of a (NC, X, Y, Z) fp32 field with a box of (nc, 1, rows, zw) elements, through the
+// driver entry point (no link-time dependency on libcuda). false when the driver does not provide it.
+inline bool make_field_tmap(CUtensorMap* tm, const void* base, long long NC, long long X, long long Y, long long Z,
+                            unsigned nc, unsigned rows, unsigned zw) {
+  typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Encode enc = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return (Encode)f;
+  }();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)NC};
+  const cuuint64_t strides[3] = {(cuuint64_t)Z * 4, (cuuint64_t)Y * Z * 4, (cuuint64_t)X * Y * Z * 4};
+  const cuuint32_t box[4] = {zw, rows, 1, nc};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace lgm

@@ -3,7 +3,6 @@
 The 256 x 256 slabs go through the 4-CTA cluster kernels (DSMEM all-to-all, csrc/fluid.cu) for beta != 0 or
 X < 64, through the quarter-slab kernels (csrc/qslab.cuh) otherwise."""
 import os, sys
-os.environ["LGM_ADSTAR_RING_256"] = "1"   # also the (slower, off by default) 256-row instance of the Ad_star ring
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import lagomorph_b200 as lm

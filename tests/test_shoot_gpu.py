@@ -96,6 +96,9 @@ for i, sh in enumerate([(8, 16, 32), (20, 24, 64), (16, 40, 128), (8, 12, 256), 
     u = (torch.rand((2, 3) + sh, generator=g) - 0.5) * 6.0      # |ds*u| < 0.3 voxel with ds = -0.1
     u[0, :, :, :2, 5:9] *= 8.0                                   # a patch that leaves the staged window
     u[1, 0, -1] += 30.0                                          # samples pushed across the x border
+    if sh[2] == 256:
+        u[0, 2, :, 4:6, 118:140] *= 40.0                         # across the seam of the two z tiles, past their halo
+        u[1, 2, :, :, 250:] += 25.0                              # clamped at the upper z border
     v = torch.randn((2, 3) + sh, generator=g)
     outs["c%d" % i] = lm.compose(u.cuda(), v.cuda(), ds=-0.1, dt=1.0).cpu()
     outs["d%d" % i] = lm.compose_disp_vel(v.cuda(), u.cuda(), dt=0.05).cpu()
