@@ -332,6 +332,13 @@ def _ramp_chunks(N):
     return [c for c in sizes if c > 0]
 
 
+def _pair_chunks(N):
+    """1, 1, 2, 2, ..., 2, 1, 1: pairs in the middle, single subjects at both ends (whose copies are exposed)"""
+    if N < 4:
+        return [1] * N
+    return [1, 1] + [2] * ((N - 4) // 2) + [1] * ((N - 4) % 2) + [1, 1]
+
+
 _BEST_CHUNKS = {}   # (device, subject shape, dtype, steps, N, streams) -> (chunk schedule, compute streams) measured best
 
 
@@ -355,8 +362,7 @@ def _measured_chunks(metric, m0_host, T, num_steps, out, dev, streams=None):
         cands.append((ramp, one))
     if N >= 4 and (streams is None or one > 1):
         two = 2 if streams is None else one
-        pairs = [1, 1] + [2] * ((N - 4) // 2) + [1] * ((N - 4) % 2) + [1, 1]
-        for sizes in (ramp, pairs, [1] * N):
+        for sizes in (ramp, _pair_chunks(N), [1] * N):
             if (sizes, two) not in cands:
                 cands.append((sizes, two))
     if len(cands) == 1 or torch.cuda.is_current_stream_capturing():

@@ -102,6 +102,12 @@ def test_expmap_host_chunk_schedule(lm):
     for N in range(1, 80):
         c = _ramp_chunks(N)
         assert sum(c) == N and min(c) >= 1 and c == sorted(c[:len(c) // 2 + 1]) + sorted(c[len(c) // 2 + 1:], reverse=True), (N, c)
+    # the two-stream candidates: pairs with single subjects at both ends, and single subjects throughout
+    from lagomorph_b200.lddmm import _pair_chunks
+    assert _pair_chunks(16) == [1, 1, 2, 2, 2, 2, 2, 2, 1, 1] and _pair_chunks(7) == [1, 1, 2, 1, 1, 1]
+    for N in range(1, 40):
+        c = _pair_chunks(N)
+        assert sum(c) == N and min(c) >= 1 and max(c) <= 2 and c[0] == 1 and c[-1] == 1, (N, c)
     with pytest.raises(RuntimeError, match="host tensors"):
         lm.expmap_host(lm.FluidMetric(), torch.zeros(1, 3, 4, 4, 4, device="meta") if False else _FakeCuda())
 

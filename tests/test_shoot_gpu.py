@@ -249,14 +249,20 @@ def test_ring_adstar_bit_identical_to_planar_kernel(tmp_path):
     script = tmp_path / "aring.py"
     script.write_text("import sys\nsys.path.insert(0, %r)\n" % os.path.join(root, "tests") + _ARING_SCRIPT)
     res = {}
-    for tag, env in (("ring", {"LGM_ADSTAR_RING_256": "1"}), ("planar", {"LGM_NO_ADSTAR_RING": "1"})):
+    # ring: the defaults (256-voxel rows as z tiles staged by TMA tensor copies); rows: the z tiles with one
+    # bulk copy per staged row (the path taken without a tensor-map entry point); wide: round 2's full rows
+    variants = (("ring", {}), ("rows", {"LGM_ADSTAR_RING_TMAP": "0"}), ("wide", {"LGM_ADSTAR_RING_256": "2"}),
+                ("planar", {"LGM_NO_ADSTAR_RING": "1"}))
+    for tag, env in variants:
         out = str(tmp_path / (tag + ".pt"))
         e = dict(os.environ)
-        e.pop("LGM_NO_ADSTAR_RING", None)
+        for k in ("LGM_NO_ADSTAR_RING", "LGM_ADSTAR_RING_256", "LGM_ADSTAR_RING_TMAP"):
+            e.pop(k, None)
         e.update(env)
         subprocess.check_call([sys.executable, str(script), out, root], env=e)
         res[tag] = torch.load(out)
     assert res["ring"].keys() == res["planar"].keys() and len(res["ring"]) == 6
-    for k in res["ring"]:
-        assert torch.isfinite(res["ring"][k]).all()
-        assert torch.equal(res["ring"][k], res["planar"][k]), k
+    for tag in ("ring", "rows", "wide"):
+        for k in res[tag]:
+            assert torch.isfinite(res[tag][k]).all()
+            assert torch.equal(res[tag][k], res["planar"][k]), (tag, k)
