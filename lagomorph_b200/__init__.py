@@ -15,7 +15,7 @@ from .lddmm import expmap, expmap_advect, expmap_host, EPDiff_step, EPDiffStep, 
 from .affine import (regrid, RegridFunction, RegridModule, affine_interp, AffineInterp,
                      AffineInterpFunction, affine_inverse, det_2x2)
 from .atlas import LDDMMAtlasBuilder, lddmm_atlas
-from .affine_atlas import affine_atlas, StandardizedDataset
+from .affine_atlas import affine_atlas, StandardizedDataset, save_affine_atlas, load_affine_atlas
 
 __version__ = "0.1.0"
 

@@ -159,3 +159,48 @@ class StandardizedDataset:
         if J.dtype not in (torch.float32, torch.float64):
             J = J.float()
         return affine_interp(J, Ainv.to(J.dtype), Tinv.to(J.dtype)).squeeze(0)
+
+
+_HDF5_MAGIC = b"\x89HDF\r\n\x1a\n"
+
+
+def save_affine_atlas(filename, I, As, Ts, epoch_losses, iter_losses):
+    """Write the result of affine_atlas() the way the reference's command does (affine.py:579-587): datasets
+    "atlas", "A", "T", "epoch_losses", "iter_losses" in one HDF5 file -- through h5py when it is importable
+    and the name ends in .h5 / .hdf5 / .hdf; otherwise the same fields through torch.save."""
+    fields = {"atlas": I.detach().cpu(), "A": As.detach().cpu(), "T": Ts.detach().cpu(),
+              "epoch_losses": [float(x) for x in epoch_losses], "iter_losses": [float(x) for x in iter_losses]}
+    if str(filename).lower().endswith((".h5", ".hdf5", ".hdf")):
+        try:
+            import h5py
+        except ImportError:
+            h5py = None
+        if h5py is not None:
+            import numpy as np
+            with h5py.File(filename, "w") as f:
+                for k in ("atlas", "A", "T"):
+                    f.create_dataset(k, data=fields[k].numpy())
+                for k in ("epoch_losses", "iter_losses"):
+                    f.create_dataset(k, data=np.asarray(fields[k], dtype=np.float64))
+            return
+    torch.save(fields, filename)
+
+
+def load_affine_atlas(filename):
+    """(I, As, Ts, epoch_losses, iter_losses) from a file written by save_affine_atlas() or by the
+    reference (HDF5, told apart by its signature)."""
+    with open(filename, "rb") as fh:
+        is_hdf5 = fh.read(8) == _HDF5_MAGIC
+    if is_hdf5:
+        try:
+            import h5py
+        except ImportError as e:
+            raise RuntimeError("%s is an HDF5 file and h5py is not installed" % filename) from e
+        import numpy as np
+        with h5py.File(filename, "r") as f:
+            t = {k: torch.as_tensor(np.asarray(f[k])) for k in ("atlas", "A", "T")}
+            el = [float(x) for x in np.asarray(f["epoch_losses"])]
+            il = [float(x) for x in np.asarray(f["iter_losses"])]
+        return t["atlas"], t["A"], t["T"], el, il
+    f = torch.load(filename, map_location="cpu")
+    return f["atlas"], f["A"], f["T"], list(f["epoch_losses"]), list(f["iter_losses"])

@@ -224,3 +224,23 @@ def test_checkpoint_hdf5_layout(tmp_path, monkeypatch):
     c = _make_builder(1, 0, data)
     c.load(name)
     assert torch.equal(c.I0, b.I0)
+
+
+def test_affine_atlas_file_roundtrip(tmp_path, monkeypatch):
+    """save_affine_atlas / load_affine_atlas: the reference's fields (affine.py:579-587), HDF5 through a stand-in
+    h5py module and torch.save without it"""
+    import types
+    from lagomorph_b200.affine_atlas import save_affine_atlas, load_affine_atlas
+    torch.manual_seed(5)
+    I, A, T = torch.randn(1, 1, 6, 5), torch.randn(4, 2, 2), torch.randn(4, 2)
+    el, il = [3.0, 2.0], [3.5, 3.0, 2.5, 2.0]
+    fake = types.ModuleType("h5py")
+    fake.File = _FakeH5File
+    for mod, name in ((fake, "a.h5"), (None, "b.h5"), (fake, "c.pt")):
+        monkeypatch.setitem(sys.modules, "h5py", mod)
+        fn = str(tmp_path / name)
+        save_affine_atlas(fn, I, A, T, el, il)
+        with open(fn, "rb") as fh:
+            assert (fh.read(8) == _FakeH5File.MAGIC) == (mod is not None and name.endswith(".h5"))
+        I2, A2, T2, el2, il2 = load_affine_atlas(fn)
+        assert torch.equal(I2, I) and torch.equal(A2, A) and torch.equal(T2, T) and el2 == el and il2 == il
