@@ -348,7 +348,7 @@ def _measured_chunks(metric, m0_host, T, num_steps, out, dev, streams=None):
     copy/compute model (_auto_chunks) and the ramp (_ramp_chunks) on one compute stream, and -- when the
     caller leaves `streams` open -- the ramp, pairs and single subjects on two. (The model assumes a shoot's
     time is proportional to its batch; small chunks are slower than that on ONE stream because none of their
-    ~50 launches fills the GPU, but two of them in flight do: C2 on a B200, r3_e2e_streams.log:
+    ~50 launches fills the GPU, but two of them in flight do: C2 on a B200, profiles/r2_e2e_streams.log:
     ramp x 1 stream 14.07 ms, single subjects x 1 stream 16.1 ms, single subjects x 2 streams 12.6 ms.)"""
     N = m0_host.shape[0]
     key = (dev.index, tuple(m0_host.shape[1:]), m0_host.dtype, int(num_steps), N, streams)
@@ -370,16 +370,20 @@ def _measured_chunks(metric, m0_host, T, num_steps, out, dev, streams=None):
     best, best_ms = cands[0], None
     for sizes, ns in cands:
         expmap_host(metric, m0_host, T=T, num_steps=num_steps, out=out, device=dev, chunk=sizes, streams=ns)   # plan, warm-up
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(dev)
-        e0.record()
-        expmap_host(metric, m0_host, T=T, num_steps=num_steps, out=out, device=dev, chunk=sizes, streams=ns)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1)
+        ms = None
+        for _ in range(2):      # best of two: one run is ~1.3 x the shoot, candidates differ by a few per cent
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            expmap_host(metric, m0_host, T=T, num_steps=num_steps, out=out, device=dev, chunk=sizes, streams=ns)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            t = e0.elapsed_time(e1)
+            ms = t if ms is None else min(ms, t)
         if best_ms is None or ms < best_ms:
             best, best_ms = (sizes, ns), ms
-    for k in [k for k in _HOST_PLANS if k[-2] != tuple(best[0]) or k[-1] != best[1] + 2]:
+    mine = (dev.index, tuple(m0_host.shape[1:]), m0_host.dtype, int(num_steps))
+    for k in [k for k in _HOST_PLANS if k[:4] == mine and (k[-2] != tuple(best[0]) or k[-1] != best[1] + 2)]:
         _HOST_PLANS.pop(k)            # the losing candidates' graphs and buffers
     _BEST_CHUNKS[key] = best
     return best
