@@ -81,6 +81,34 @@ def test_interp_backward_fullsize_vs_reference_kernels(lm, ref, N, n):
     assert relerr(Ic.grad, dI_r) <= 1e-4
 
 
+@pytest.mark.parametrize("N,n", [(1, 128), (1, 256)])
+def test_stress_variant_vs_reference_kernels(lm, ref, N, n):
+    """SURVEY 8(d) stress variant: white-noise displacement uniform in +-8 voxels plus border bands pushed
+    +-(n + 2) voxels out of range -- no locality for the gathers (every warp of the staged-ring kernels leaves
+    its window or sits at a clamped border), all splats of a band land on one face (atomic contention)."""
+    sh = (n, n, n)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    u = (torch.rand((N, 3) + sh, device="cuda", generator=g) - 0.5) * 16.0
+    u[:, 0, :3] -= n + 2
+    u[:, 1, :, -3:] += n + 2
+    u[:, 2, :, :, :2] -= n + 2
+    u[:, 2, :, :, -2:] += n + 2
+    m = torch.randn((N, 3) + sh, device="cuda", generator=g)
+    assert relerr(lm.Ad_star(u, m), ref.Ad_star(u, m)) <= 1e-5
+    assert relerr(lm.compose(m, u, ds=1.0, dt=1.0), ref.compose(m, u, 1.0, 1.0)) <= 1e-5
+    assert relerr(lm.compose(u, m, ds=-0.1, dt=1.0), ref.compose(u, m, -0.1, 1.0)) <= 1e-5   # ring kernel, all fallbacks
+    I = m[:, :1].contiguous()
+    go = torch.randn((N, 1) + sh, device="cuda", generator=g)
+    assert relerr(lm.interp(I, u), ref.rc.interp_fwd(I, u, 1.0)) <= 1e-5
+    dI_r, du_r = ref.rc.interp_bwd(go, I, u, 1.0)
+    Ic, uc = I.clone().requires_grad_(True), u.clone().requires_grad_(True)
+    lm.interp(Ic, uc).backward(go)
+    assert relerr(uc.grad, du_r) <= 1e-5
+    s, sr = Ic.grad.double().sum().item(), dI_r.double().sum().item()
+    assert abs(s - sr) <= 1e-5 * go.double().abs().sum().item()
+    assert relerr(Ic.grad, dI_r) <= 1e-4
+
+
 def test_affine_interp_c4_vs_reference_kernels(lm, ref):
     """BASELINE config 4 at its grid (192^3), 2 subjects: forward and d_I, d_A, d_T."""
     N, sh = 2, (192, 192, 192)
