@@ -126,7 +126,7 @@ __device__ __forceinline__ void dft4_inv(float2& a0, float2& a1, float2& a2, flo
 //   lxq  : 2(1-cos) of the X frequency held by tile row rho = k1*8 + k2  (kx = k1 + (NX/8) k2)
 //   wyq  : [r][kpos] 2(1-cos) of the Y frequency fft_freq<YQ>(kpos) + YQ r
 //   wlz  : Z LUT in the storage order of the real transform
-template <int NX, int YQ, bool INVERSE>
+template <int NX, int YQ, bool INVERSE, bool SAFE = false>
 __global__ void __launch_bounds__(kQxThreads, LGM_XPASSQ_MINBLOCKS)
 xpassq_kernel(float2* __restrict__ spec, int Zc, const float2* __restrict__ twx_g, const float2* __restrict__ twy_g,
               const float* __restrict__ lxq, const float* __restrict__ wyq, const float* __restrict__ wlz,
@@ -218,7 +218,7 @@ xpassq_kernel(float2* __restrict__ spec, int Zc, const float2* __restrict__ twx_
         const float Lm = lambda * lambda;
         C u = a[r];
         if (INVERSE) {
-          const float f = oo_lambda_fast<float>(lambda, Lm);
+          const float f = oo_lambda_fast<float, SAFE>(lambda, Lm);
           u.x = ((u.x * f) * f) * scale;
           u.y = ((u.y * f) * f) * scale;
         } else {

@@ -221,6 +221,50 @@ def test_quarter_slab_path_matches_cluster_path(tmp_path):
         assert ((a - b).norm() / b.norm()).item() <= 1e-6, k
 
 
+_SAFE_SCRIPT = """
+import sys, torch
+sys.path.insert(0, sys.argv[2])
+import lagomorph_b200 as lm
+outs = {}
+g = torch.Generator().manual_seed(19)
+for name, sh, params in (("c128", (2, 3, 128, 128, 128), [0.1, 0.0, 0.01]), ("q256", (1, 3, 64, 256, 256), [0.1, 0.0, 0.01]),
+                         ("x64", (2, 3, 64, 32, 64), [0.5, 0.0, 0.5]), ("x512", (1, 3, 512, 16, 32), [0.1, 0.0, 0.001]),
+                         ("2d", (3, 2, 128, 128), [0.1, 0.0, 0.01]), ("edge", (1, 3, 32, 32, 32), [1e14, 0.0, 2e-4]),
+                         ("tiny", (1, 3, 32, 32, 32), [0.1, 0.0, 1e-5])):
+    m = torch.randn(sh, generator=g).cuda()
+    met = lm.FluidMetric(params)
+    outs[name] = met.sharp(m).cpu()
+    outs[name + "_rt"] = met.flat(met.sharp(m)).cpu()
+torch.save(outs, sys.argv[1])
+"""
+
+
+def test_safe_range_multiplier_bit_identical(tmp_path):
+    """beta == 0, fp32: when the host can bound lambda = gamma + alpha * sw inside [2e-4, 1e15] the X passes run
+    the multiplier without its safe_sqrt selects and without the reciprocal's range test (csrc/fluid.cu
+    lambda_range_safe / oo_lambda_fast<R, true>). Same bits as the guarded form (LGM_NO_SAFE_LAMBDA=1, read once
+    per process: two subprocesses) on the 128^2 slab path, the quarter slabs, two- and three-stage X transforms,
+    2-D, parameters at the edge of the range, and parameters outside it (gamma = 1e-5: guarded form either way)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "safe.py"
+    script.write_text(_SAFE_SCRIPT)
+    res = {}
+    for tag, env in (("safe", {}), ("guarded", {"LGM_NO_SAFE_LAMBDA": "1"})):
+        out = str(tmp_path / (tag + ".pt"))
+        e = dict(os.environ)
+        e.pop("LGM_NO_SAFE_LAMBDA", None)
+        e.update(env)
+        subprocess.check_call([sys.executable, str(script), out, root], env=e)
+        res[tag] = torch.load(out)
+    assert res["safe"].keys() == res["guarded"].keys() and len(res["safe"]) == 14
+    for k in res["safe"]:
+        assert torch.isfinite(res["safe"][k]).all(), k
+        assert torch.equal(res["safe"][k], res["guarded"][k]), k
+
+
 _ARING_SCRIPT = """
 import sys, torch
 sys.path.insert(0, sys.argv[2])
